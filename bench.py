@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload black_scholes|stencil] [--impl reference]
+
+Own arm: one "step" is one pass of the workload over one batch of synthetic input resident in HBM:
+  black_scholes (default, BASELINE.json configs[1]): examples/black_scholes.py fp32, 1e8 options per
+      GPU — 63 elementwise tasks per step, issued op-by-op through the cunumeric NumPy API exactly
+      as the reference issues them.  metric = options (elements) per second.
+  stencil (configs[3]): examples/stencil.py fp64 N=40000 row-partitioned over the GPUs, ITERS
+      Jacobi iterations per step (6 tasks each), halo rows exchanged over NVLink.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU arithmetic
+(oracle/_ref: its functor headers compiled with g++, OpenMP over all host cores) on a bounded
+sample of the same workload."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "black_scholes_elements_per_second"
+UNIT = "options/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="own", choices=["own", "reference"])
+    p.add_argument("--workload", default="black_scholes", choices=["black_scholes", "stencil"])
+    p.add_argument("--n", type=int, default=100_000_000, help="options per GPU (black_scholes)")
+    p.add_argument("--stencil-n", type=int, default=40000)
+    p.add_argument("--stencil-iters", type=int, default=10, help="Jacobi iterations per step")
+    p.add_argument("--cpu-sample", type=int, default=10_000_000,
+                   help="options in the bounded CPU-baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int) -> None:
+        self.device = device
+        self.proc = None
+        self.tmp = None
+
+    def start(self) -> None:
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.device)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": the upper half of the samples (idle samples before/after drag the median)
+        loaded = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(smax),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(world: int):
+    """Plumbing only: torch.distributed (gloo) for barrier + max-over-ranks of the device timings,
+    and to hand rank 0's NCCL unique id to the others."""
+    rank = int(os.environ.get("RANK", "0"))
+    if world == 1:
+        return rank, None
+    import torch.distributed as dist
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    return rank, dist
+
+
+def barrier(dist) -> None:
+    if dist is not None:
+        dist.barrier()
+
+
+def max_over_ranks(dist, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_black_scholes(n_sample: int, reps: int = 2) -> dict:
+    from oracle import ref, refnp
+    from cunumeric_b200.workloads import black_scholes, black_scholes_inputs
+
+    cores = os.cpu_count() or 1
+    refnp.set_threads(cores)
+    S, X, T = black_scholes_inputs(n_sample, np.float32, seed=0)
+    S, X, T = refnp.array(S), refnp.array(X), refnp.array(T)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        black_scholes(S, X, T, 0.02, 0.3, xp=refnp)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": n_sample / best, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{n_sample} options, best of {reps}; reference functors (oracle/_ref, "
+                      f"g++ -O2 -fopenmp, schedule(static)) op-by-op, 63 tasks",
+            "available": ref.available()}
+
+
+def run_reference(args) -> None:
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refnp
+    from cunumeric_b200.workloads import black_scholes, black_scholes_inputs
+
+    cores = os.cpu_count() or 1
+    refnp.set_threads(cores)
+    n = args.cpu_sample
+    S, X, T = black_scholes_inputs(n, np.float32, seed=0)
+    S, X, T = refnp.array(S), refnp.array(X), refnp.array(T)
+    for _ in range(min(args.warmup, 2)):
+        black_scholes(S, X, T, 0.02, 0.3, xp=refnp)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        black_scholes(S, X, T, 0.02, 0.3, xp=refnp)
+    dt = time.perf_counter() - t0
+    value = n * steps / dt
+    sample = (f"{n} options per step (bounded sample of the 1e8-option workload), {steps} steps; "
+              "reference functors compiled from /root/reference/src (oracle/_ref), OpenMP")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "black_scholes fp32 (examples/black_scholes.py), op-by-op",
+                   "options_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def trace_summary(cn, n_records: int, peak_gbs: float):
+    """Group the live per-launch records by kernel (task, op, dtype) and pick the dominant one."""
+    import ctypes
+
+    from cunumeric_b200 import _lib
+
+    lib = cn.runtime.lib
+    groups = {}
+    rec = _lib.cnb_trace_record_t()
+    total_ms = 0.0
+    for i in range(n_records):
+        _lib.check(lib.cnb_trace_get(i, ctypes.byref(rec)))
+        key = (rec.task, rec.op, rec.dtype)
+        g = groups.setdefault(key, {"launches": 0, "ms": 0.0, "bytes": 0})
+        g["launches"] += 1
+        g["ms"] += rec.ms
+        g["bytes"] += rec.bytes
+        total_ms += rec.ms
+    if not groups:
+        return None, {}
+    top_key, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+    names = {5: "BINARY_OP", 43: "UNARY_OP", 49: "WHERE", 11: "CONVERT", 33: "SCALAR_UNARY_RED",
+             44: "UNARY_RED", 19: "FILL"}
+    from cunumeric_b200.config import BinaryOpCode, UnaryOpCode
+
+    opname = str(top_key[1])
+    if top_key[0] == 5:
+        opname = BinaryOpCode(top_key[1]).name
+    elif top_key[0] == 43:
+        opname = UnaryOpCode(top_key[1]).name
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "frac": achieved / peak_gbs, "traffic": None,
+        "kernel": f"ew_kernel<{names.get(top_key[0], top_key[0])}:{opname}:dtype{top_key[2]}>",
+        "launches": top["launches"],
+        "avg_launch_ms": top["ms"] / top["launches"],
+        "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
+        "share_of_step": top["ms"] / total_ms,
+    }
+    all_bytes = sum(g["bytes"] for g in groups.values())
+    whole = {"kernel_ms_total": total_ms, "algorithmic_gbs_all_kernels": all_bytes / (total_ms * 1e-3) / 1e9,
+             "frac_all_kernels": all_bytes / (total_ms * 1e-3) / 1e9 / peak_gbs}
+    return roofline, whole
+
+
+def run_black_scholes(args, rank: int, world: int, dist) -> None:
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import _lib
+    from cunumeric_b200.workloads import (BLACK_SCHOLES_BYTES_PER_OPTION_F32, BLACK_SCHOLES_TASKS,
+                                          black_scholes, black_scholes_inputs)
+
+    n = args.n
+    cn.runtime.ensure_initialized()
+    lib = cn.runtime.lib
+    peak_gbs, peak_src = load_peaks()
+    R, V = 0.02, 0.3
+    # synthetic inputs, generated on the host once, staged in PINNED memory (for the e2e leg) and
+    # made resident in HBM before the timed region
+    Sh, Xh, Th = (cn.pinned_empty(n, np.float32) for _ in range(3))
+    for dst, src in zip((Sh, Xh, Th), black_scholes_inputs(n, np.float32, seed=rank)):
+        dst[...] = src
+    S, X, T = cn.array(Sh), cn.array(Xh), cn.array(Th)
+    cn.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        call, put = black_scholes(S, X, T, R, V)
+    cn.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides
+    ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
+    sampler = ClockSampler(cn.runtime.device)
+    sampler.start()
+    time.sleep(0.3)
+    _lib.check(lib.cnb_trace_start(args.steps * (BLACK_SCHOLES_TASKS + 8)))
+    barrier(dist)
+    cn.synchronize()
+    launches0 = cn.runtime.launch_count()
+    lib.cnb_event_record(ev0, cn.runtime.stream)
+    for _ in range(args.steps):
+        call, put = black_scholes(S, X, T, R, V)
+    lib.cnb_event_record(ev1, cn.runtime.stream)
+    cn.synchronize()
+    barrier(dist)
+    launches = cn.runtime.launch_count() - launches0
+    n_rec = lib.cnb_trace_stop()
+    import ctypes
+
+    ms = ctypes.c_float()
+    _lib.check(lib.cnb_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+    clocks = sampler.stop()
+    elapsed = max_over_ranks(dist, ms.value * 1e-3)
+    value = n * world * args.steps / elapsed
+    roofline, whole = trace_summary(cn, n_rec, peak_gbs)
+    if roofline is not None:
+        roofline["peak_source"] = peak_src
+        roofline.update(whole)
+
+    # ---- e2e: the same step through the public API from HOST buffers (pinned), copies inside
+    e2e = None
+    if not args.no_e2e:
+        call_h, put_h = cn.pinned_empty(n, np.float32), cn.pinned_empty(n, np.float32)
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            s, x, t = cn.array(Sh), cn.array(Xh), cn.array(Th)
+            c, p = black_scholes(s, x, t, R, V)
+            c.to_host(call_h)
+            p.to_host(put_h)
+
+        e2e_step()
+        barrier(dist)
+        cn.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        cn.synchronize()
+        dt = max_over_ranks(dist, time.perf_counter() - t0)
+        e2e = {"value": n * world * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": 3 * 4 * n, "d2h_bytes_per_step": 2 * 4 * n,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": "cunumeric_b200.array(pinned) -> black_scholes() -> ndarray.to_host(pinned)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_black_scholes(args.cpu_sample)
+        except Exception as exc:  # the checker is optional for the measurement itself
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                   "sample": f"unavailable: {exc}"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "black_scholes fp32 1e8 options per GPU "
+                                   "(examples/black_scholes.py, BASELINE.json configs[1]), "
+                                   "63 elementwise tasks per step issued op-by-op",
+                       "options_per_gpu": n, "tasks_per_step": BLACK_SCHOLES_TASKS,
+                       "algorithmic_bytes_per_option": BLACK_SCHOLES_BYTES_PER_OPTION_F32,
+                       "l2_policy": "inputs and every temporary are 400 MB, larger than the "
+                                    "126 MB L2; no flush needed",
+                       "whole_step_algorithmic_gbs":
+                           BLACK_SCHOLES_BYTES_PER_OPTION_F32 * n * args.steps / elapsed / 1e9},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e,
+        }))
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched without torchrun: re-exec under it (one rank per GPU)
+        port = os.environ.get("MASTER_PORT", "29511")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", port,
+               os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, dist = dist_setup(world)
+    if args.workload == "black_scholes":
+        run_black_scholes(args, rank, world, dist)
+    else:
+        from cunumeric_b200.bench_stencil import run_stencil
+
+        run_stencil(args, rank, world, dist, ClockSampler, load_peaks, max_over_ranks, barrier)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

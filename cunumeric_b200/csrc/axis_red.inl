@@ -1,0 +1,433 @@
+// UNARY_RED (single-axis reduction) for sm_100a, included by axis_red_g*.cu.
+//
+// The launcher canonicalises the task into  kept dims (<=3, merged, fastest last) x axis  using the
+// real byte strides, so transposed / sliced inputs pick their mode from the memory layout, not from
+// the logical axis number:
+//   COLUMN mode (a kept dim is the contiguous one, e.g. axis 0 of a C-order matrix): lanes run
+//     along the contiguous kept dim with 128-bit loads, the 8 warps of a CTA stride over the axis,
+//     the axis is split across gridDim.y CTAs for occupancy; partials meet in shared memory, split
+//     partials in a scratch buffer that the last-arriving CTA of each column tile folds IN SPLIT
+//     ORDER.  No atomics on data — the reference finishes every thread with a global atomic /
+//     CAS loop (unary_red.cu:298-312, arg.inl:52-82).
+//   ROW mode (the axis itself is contiguous, e.g. axis 1): one CTA (long rows) or one warp (short
+//     rows) per output element, 128-bit loads along the axis, shuffle + shared-memory fold.
+// Results are folded into the caller's pre-filled output store (reduce-accessor semantics).
+#include "cnb_reduce.cuh"
+#include "ops_reduce.cuh"
+
+#include <algorithm>
+
+namespace cnb {
+
+void* pool_alloc(size_t nbytes, cudaStream_t stream);
+int pool_free(void* p, cudaStream_t stream);
+
+namespace {
+
+constexpr int AX_KEPT = 3;
+
+struct AxisPlan {
+  long long kept[AX_KEPT];       // kept extents, slowest first, right-aligned, padded with 1
+  long long in_k[AX_KEPT];       // byte strides of `in` over kept dims
+  long long out_k[AX_KEPT];      // byte strides of `out`
+  long long w_k[AX_KEPT];        // byte strides of `where`
+  long long alen, in_a, w_a;     // axis extent and strides
+  long long axis_origin;
+  long long ncols;               // product of kept
+  const char* in;
+  const char* where;             // nullptr = no mask
+  char* out;
+  int vec;                       // vector loads legal along the lane dimension
+  // column mode
+  long long tiles_fast;          // column tiles along kept[2]
+  long long split_len;           // axis rows per split
+  int nsplit;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class R, int V>
+__device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, char* scratch_raw,
+                                              unsigned int* tickets)
+{
+  using T   = typename R::In;
+  using Acc = typename R::Acc;
+  using Val = typename R::Val;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+
+  // column tile -> (position along the fast kept dim, index over the slower kept dims)
+  const long long tile  = blockIdx.x;
+  const long long slow  = tile / p.tiles_fast;
+  const long long tfast = tile - slow * p.tiles_fast;
+  const long long k1    = slow % p.kept[1];
+  const long long k0    = slow / p.kept[1];
+  const long long c0    = tfast * (32 * V) + (long long)tx * V;  // first column of this lane
+  const bool active     = c0 < p.kept[2];
+  const long long in_base  = k0 * p.in_k[0] + k1 * p.in_k[1] + c0 * p.in_k[2];
+  const long long w_base   = k0 * p.w_k[0] + k1 * p.w_k[1] + c0 * p.w_k[2];
+  const long long out_base = k0 * p.out_k[0] + k1 * p.out_k[1] + c0 * p.out_k[2];
+  const int nvalid = active ? (int)min((long long)V, p.kept[2] - c0) : 0;
+
+  Acc acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = R::identity();
+
+  const long long a_begin = (long long)blockIdx.y * p.split_len;
+  const long long a_end   = min(p.alen, a_begin + p.split_len);
+  constexpr int UNR       = 4;
+  if (active) {
+    for (long long a0 = a_begin + ty; a0 < a_end; a0 += RED_WARPS * UNR) {
+      Pack<T, V> x[UNR];
+      bool ok[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const long long a = a0 + (long long)u * RED_WARPS;
+        ok[u]             = a < a_end;
+        if (ok[u]) {
+          const char* src = p.in + in_base + a * p.in_a;
+          if constexpr (V > 1) {
+            ld_bytes<sizeof(T) * V>(x[u].raw, src);
+          } else {
+            ld_bytes<sizeof(T)>(x[u].raw, src);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (ok[u]) {
+          const long long a = a0 + (long long)u * RED_WARPS;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            bool m = v < nvalid;
+            if (m && p.where != nullptr)
+              m = *reinterpret_cast<const unsigned char*>(p.where + w_base + v * p.w_k[2] +
+                                                          a * p.w_a) != 0;
+            if (m) acc[v] = R::fold(acc[v], r.convert(x[u][v], p.axis_origin + a));
+          }
+        }
+      }
+    }
+  }
+
+  // fold the 8 row-lanes of the CTA in ty order
+  __shared__ RawSmem<Acc, RED_WARPS * 32 * V> smem;
+  Acc* sm = smem.ptr();
+#pragma unroll
+  for (int v = 0; v < V; ++v) sm[(ty * 32 + tx) * V + v] = acc[v];
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      Acc t = sm[tx * V + v];
+      for (int w = 1; w < RED_WARPS; ++w) t = R::fold(t, sm[(w * 32 + tx) * V + v]);
+      acc[v] = t;
+    }
+  }
+
+  if (p.nsplit == 1) {
+    if (ty == 0) {
+      for (int v = 0; v < nvalid; ++v) {
+        Val* o = reinterpret_cast<Val*>(p.out + out_base + v * p.out_k[2]);
+        *o     = R::finish(R::fold(R::lift(*o), acc[v]));
+      }
+    }
+    return;
+  }
+
+  // split partials -> scratch[split][tile][32*V]; last CTA of the tile folds them in split order
+  Acc* scratch            = reinterpret_cast<Acc*>(scratch_raw);
+  const long long per_spl = (long long)gridDim.x * 32 * V;
+  if (ty == 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      scratch[(long long)blockIdx.y * per_spl + tile * 32 * V + tx * V + v] = acc[v];
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[tile], 1u);
+    is_last              = (t == (unsigned int)p.nsplit - 1);
+  }
+  __syncthreads();
+  if (is_last && ty == 0) {
+    __threadfence();
+    for (int v = 0; v < nvalid; ++v) {
+      Acc t = R::identity();
+      for (int s = 0; s < p.nsplit; ++s) {
+        Acc q;
+        ld_bytes<sizeof(Acc)>(&q, reinterpret_cast<const char*>(
+                                    &scratch[(long long)s * per_spl + tile * 32 * V + tx * V + v]));
+        t = R::fold(t, q);
+      }
+      Val* o = reinterpret_cast<Val*>(p.out + out_base + v * p.out_k[2]);
+      *o     = R::finish(R::fold(R::lift(*o), t));
+    }
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(RED_THREADS)
+axis_col_kernel(const __grid_constant__ AxisPlan p, const R r, char* scratch, unsigned int* tickets)
+{
+  constexpr int V = (16 / sizeof(typename R::In)) > 4 ? 4 : ((16 / sizeof(typename R::In)) < 1 ? 1 : 16 / sizeof(typename R::In));
+  if (p.vec) {
+    if constexpr (V > 1) axis_col_body<R, V>(p, r, scratch, tickets);
+  } else {
+    axis_col_body<R, 1>(p, r, scratch, tickets);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ROW mode: LPR lanes cooperate on one output element (LPR = 32: a warp, LPR = 256: the CTA)
+template <class R, int LPR>
+__global__ void __launch_bounds__(RED_THREADS)
+axis_row_kernel(const __grid_constant__ AxisPlan p, const R r)
+{
+  using T   = typename R::In;
+  using Acc = typename R::Acc;
+  using Val = typename R::Val;
+  constexpr int V    = (16 / sizeof(T)) < 1 ? 1 : 16 / sizeof(T);
+  constexpr int ROWS = RED_THREADS / LPR;  // outputs per CTA iteration
+  const int lane     = threadIdx.x % LPR;
+  const int sub      = threadIdx.x / LPR;
+  __shared__ RawSmem<Acc, RED_WARPS> smem;
+
+  const long long ngroups = (p.ncols + ROWS - 1) / ROWS;
+  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const long long c = g * ROWS + sub;
+    const bool active = c < p.ncols;
+    long long in_base = 0, w_base = 0, out_base = 0;
+    if (active) {
+      long long q        = c;
+      const long long k2 = q % p.kept[2];
+      q /= p.kept[2];
+      const long long k1 = q % p.kept[1];
+      const long long k0 = q / p.kept[1];
+      in_base            = k0 * p.in_k[0] + k1 * p.in_k[1] + k2 * p.in_k[2];
+      w_base             = k0 * p.w_k[0] + k1 * p.w_k[1] + k2 * p.w_k[2];
+      out_base           = k0 * p.out_k[0] + k1 * p.out_k[1] + k2 * p.out_k[2];
+    }
+    Acc acc = R::identity();
+    if (active) {
+      // the row start may be misaligned for 16-byte loads even when the matrix is: peel
+      long long a = 0;
+      bool vec    = p.vec && V > 1 && p.where == nullptr;
+      if (vec) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(p.in + in_base);
+        const int mis        = (int)(addr % 16);
+        long long peel       = mis ? (16 - mis) / (long long)sizeof(T) : 0;
+        peel                 = min(peel, p.alen);
+        if (lane < peel) {
+          Pack<T, 1> x;
+          ld_bytes<sizeof(T)>(x.raw, p.in + in_base + lane * (long long)sizeof(T));
+          acc = R::fold(acc, r.convert(x[0], p.axis_origin + lane));
+        }
+        a = peel;
+        constexpr int UNR   = 4;
+        const long long nv  = (p.alen - a) / V;  // full vectors
+        const char* base    = p.in + in_base + a * (long long)sizeof(T);
+        long long i         = lane;
+        for (; i + (long long)(UNR - 1) * LPR < nv; i += (long long)UNR * LPR) {
+          Pack<T, V> x[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+            ld_bytes<sizeof(T) * V>(x[u].raw, base + (i + (long long)u * LPR) * (16));
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              acc = R::fold(acc, r.convert(x[u][v],
+                                           p.axis_origin + a + (i + (long long)u * LPR) * V + v));
+        }
+        for (; i < nv; i += LPR) {
+          Pack<T, V> x;
+          ld_bytes<sizeof(T) * V>(x.raw, base + i * 16);
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            acc = R::fold(acc, r.convert(x[v], p.axis_origin + a + i * V + v));
+        }
+        a += nv * V;
+      }
+      // scalar remainder / strided / masked path
+      for (long long i = a + lane; i < p.alen; i += LPR) {
+        bool m = true;
+        if (p.where != nullptr)
+          m = *reinterpret_cast<const unsigned char*>(p.where + w_base + i * p.w_a) != 0;
+        if (m) {
+          Pack<T, 1> x;
+          ld_bytes<sizeof(T)>(x.raw, p.in + in_base + i * p.in_a);
+          acc = R::fold(acc, r.convert(x[0], p.axis_origin + i));
+        }
+      }
+    }
+    if constexpr (LPR == 32) {
+      acc = warp_reduce<R>(acc);
+    } else {
+      acc = block_reduce<R>(acc, smem.ptr());
+    }
+    if (active && lane == 0) {
+      Val* o = reinterpret_cast<Val*>(p.out + out_base);
+      *o     = R::finish(R::fold(R::lift(*o), acc));
+    }
+  }
+}
+
+template <int OP>
+int axis_red_by_type(int axis, const cnb_store_t* out, const cnb_store_t* in,
+                     const cnb_store_t* where, long long axis_origin, cudaStream_t stream)
+{
+  return type_dispatch(in->dtype, [&](auto tag) -> int {
+    using T = type_of<decltype(tag)::value>;
+    using R = typename RedFn<OP>::template fn<T>;
+    if constexpr (!R::valid || OP == CNB_RED_CONTAINS) {
+      return set_error(CNB_ERR_INVALID_OP, "UNARY_RED %d is not valid for dtype %d", OP, in->dtype);
+    } else {
+      using Acc = typename R::Acc;
+      using Val = typename R::Val;
+      const int nd = in->ndim;
+      if (nd < 1 || nd > CNB_MAX_DIM || axis < 0 || axis >= nd)
+        return set_error(CNB_ERR_BAD_ARG, "UNARY_RED: axis %d out of range for ndim %d", axis, nd);
+      if (out->ndim != nd)
+        return set_error(CNB_ERR_BAD_ARG, "UNARY_RED: out must be promoted to in's rank");
+      if (out->dtype != CodeOf<Val>::value)
+        return set_error(CNB_ERR_BAD_ARG, "UNARY_RED %d on dtype %d: out dtype %d, expected %d", OP,
+                         in->dtype, out->dtype, CodeOf<Val>::value);
+      if (where != nullptr && (where->dtype != CNB_BOOL || where->ndim != nd))
+        return set_error(CNB_ERR_BAD_ARG, "UNARY_RED: bad where mask");
+      for (int d = 0; d < nd; ++d) {
+        if (d != axis && out->shape[d] != in->shape[d])
+          return set_error(CNB_ERR_BAD_ARG, "UNARY_RED: out extent mismatch on dim %d", d);
+        if (where != nullptr && where->shape[d] != in->shape[d])
+          return set_error(CNB_ERR_BAD_ARG, "UNARY_RED: where extent mismatch on dim %d", d);
+        if (in->shape[d] == 0) return CNB_OK;  // unary_red_template.inl:47
+      }
+
+      // ---- canonicalise kept dims
+      struct Dim {
+        long long n, si, so, sw;
+      } dims[CNB_MAX_DIM];
+      int nk = 0;
+      for (int d = 0; d < nd; ++d) {
+        if (d == axis || in->shape[d] == 1) continue;
+        dims[nk++] = {in->shape[d], in->strides[d], out->strides[d], where ? where->strides[d] : 0};
+      }
+      std::stable_sort(dims, dims + nk, [](const Dim& a, const Dim& b) {
+        return std::llabs(a.si) > std::llabs(b.si);
+      });
+      int m = 0;
+      for (int d = 1; d < nk; ++d) {
+        const Dim& nx = dims[d];
+        if (dims[m].si == nx.n * nx.si && dims[m].so == nx.n * nx.so && dims[m].sw == nx.n * nx.sw) {
+          dims[m].n *= nx.n;
+          dims[m].si = nx.si;
+          dims[m].so = nx.so;
+          dims[m].sw = nx.sw;
+        } else {
+          dims[++m] = nx;
+        }
+      }
+      if (nk > 0) nk = m + 1;
+
+      AxisPlan p{};
+      for (int d = 0; d < AX_KEPT; ++d) {
+        p.kept[d] = 1;
+        p.in_k[d] = p.out_k[d] = p.w_k[d] = 0;
+      }
+      p.ncols = 1;
+      for (int d = 0; d < nk; ++d) {
+        const int slot = AX_KEPT - nk + d;
+        p.kept[slot]   = dims[d].n;
+        p.in_k[slot]   = dims[d].si;
+        p.out_k[slot]  = dims[d].so;
+        p.w_k[slot]    = dims[d].sw;
+        p.ncols *= dims[d].n;
+      }
+      p.alen        = in->shape[axis];
+      p.in_a        = in->strides[axis];
+      p.w_a         = where ? where->strides[axis] : 0;
+      p.axis_origin = axis_origin;
+      p.in          = static_cast<const char*>(in->ptr);
+      p.where       = where ? static_cast<const char*>(where->ptr) : nullptr;
+      p.out         = static_cast<char*>(out->ptr);
+      p.nsplit      = 1;
+      p.split_len   = p.alen;
+      p.tiles_fast  = 1;
+
+      const long long isz = sizeof(T);
+      // input once (+ mask) + one read-modify-write of every output element
+      const long long algo_bytes = p.ncols * p.alen * (isz + (where ? 1 : 0)) +
+                                   2 * p.ncols * (long long)sizeof(Val);
+      const bool col_mode = nk > 0 && std::llabs(p.in_k[AX_KEPT - 1]) < std::llabs(p.in_a) &&
+                            !(p.alen == 1);
+      const int sms = sm_count();
+      if (col_mode || (nk > 0 && p.alen == 1)) {
+        constexpr int V = (16 / sizeof(T)) > 4 ? 4 : ((16 / sizeof(T)) < 1 ? 1 : 16 / sizeof(T));
+        const long long vb = V * isz;
+        bool vec = V > 1 && p.in_k[2] == isz && reinterpret_cast<uintptr_t>(p.in) % vb == 0 &&
+                   p.in_a % vb == 0 && p.in_k[0] % vb == 0 && p.in_k[1] % vb == 0 &&
+                   p.kept[2] % V == 0;
+        p.vec               = vec ? 1 : 0;
+        const int lanes_w   = 32 * (vec ? V : 1);
+        p.tiles_fast        = (p.kept[2] + lanes_w - 1) / lanes_w;
+        const long long tiles = p.tiles_fast * p.kept[0] * p.kept[1];
+        if (tiles > 0x7fffffffLL) return set_error(CNB_ERR_UNSUPPORTED, "UNARY_RED: too many tiles");
+        // split the axis until ~4 CTAs per SM are in flight, keeping >= 64 rows per split
+        long long want = (4LL * sms + tiles - 1) / tiles;
+        long long maxs = std::max<long long>(1, p.alen / 64);
+        int nsplit     = (int)std::max<long long>(1, std::min<long long>(std::min(want, maxs), 65535));
+        p.split_len    = (p.alen + nsplit - 1) / nsplit;
+        nsplit         = (int)((p.alen + p.split_len - 1) / p.split_len);
+        p.nsplit       = nsplit;
+        char* scratch         = nullptr;
+        unsigned int* tickets = nullptr;
+        if (nsplit > 1) {
+          const size_t sbytes = (size_t)nsplit * tiles * lanes_w * sizeof(Acc);
+          const size_t tbytes = (size_t)tiles * sizeof(unsigned int);
+          scratch = static_cast<char*>(pool_alloc(sbytes + tbytes, stream));
+          if (scratch == nullptr) return CNB_ERR_CUDA;
+          tickets = reinterpret_cast<unsigned int*>(scratch + sbytes);
+          int rc  = check_cuda(cudaMemsetAsync(tickets, 0, tbytes, stream), "ticket memset");
+          if (rc != CNB_OK) return rc;
+        }
+        dim3 grid((unsigned)tiles, (unsigned)nsplit);
+        {
+          LaunchScope scope(stream, KERNEL_AXIS_COL, p.ncols * p.alen, algo_bytes);
+          axis_col_kernel<R><<<grid, RED_THREADS, 0, stream>>>(p, R(nullptr), scratch, tickets);
+        }
+        int rc = check_cuda(cudaGetLastError(), "axis_col_kernel launch");
+        if (scratch != nullptr) pool_free(scratch, stream);
+        return rc;
+      } else {
+        p.vec = (p.in_a == isz) ? 1 : 0;
+        LaunchScope scope(stream, KERNEL_AXIS_ROW, p.ncols * p.alen, algo_bytes);
+        if (p.alen >= 2048) {
+          auto kernel = axis_row_kernel<R, RED_THREADS>;
+          long long g = std::min<long long>(p.ncols, (long long)sms * 8);
+          kernel<<<(unsigned)std::max<long long>(1, g), RED_THREADS, 0, stream>>>(p, R(nullptr));
+        } else {
+          auto kernel    = axis_row_kernel<R, 32>;
+          long long ngrp = (p.ncols + RED_WARPS - 1) / RED_WARPS;
+          long long g    = std::min<long long>(ngrp, (long long)sms * 8);
+          kernel<<<(unsigned)std::max<long long>(1, g), RED_THREADS, 0, stream>>>(p, R(nullptr));
+        }
+        return check_cuda(cudaGetLastError(), "axis_row_kernel launch");
+      }
+    }
+  });
+}
+
+}  // namespace
+
+int CNB_ARED_GROUP_NAME(int op, int axis, const cnb_store_t* out, const cnb_store_t* in,
+                        const cnb_store_t* where, long long axis_origin, cudaStream_t stream)
+{
+  switch (op) {
+#define X(OPCODE) \
+  case OPCODE: return axis_red_by_type<OPCODE>(axis, out, in, where, axis_origin, stream);
+    CNB_ARED_GROUP_OPS(X)
+#undef X
+  }
+  return 1;
+}
+
+}  // namespace cnb

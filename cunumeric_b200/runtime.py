@@ -1,0 +1,185 @@
+"""Process-level runtime: device selection, the compute stream, device allocations, host<->device
+copies and (multi-GPU) the exchange communicator.
+
+Plays the role the reference delegates to legate.core (cunumeric/runtime.py:545 `runtime`
+singleton + Legion's allocator / StreamPool): one process drives one GPU; every task is launched
+asynchronously on `runtime.stream`; nothing synchronises until a value is read on the host."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _lib
+from .config import argval_dtype, dtype_code
+
+
+class DeviceBuffer:
+    """An owned, stream-ordered device allocation (freed back to the pool on GC)."""
+
+    __slots__ = ("ptr", "nbytes", "_runtime", "__weakref__")
+
+    def __init__(self, runtime: "Runtime", nbytes: int) -> None:
+        self._runtime = runtime
+        self.nbytes = int(nbytes)
+        self.ptr = _lib.check_ptr(runtime.lib.cnb_malloc(max(self.nbytes, 1), runtime.stream))
+
+    def __del__(self) -> None:
+        try:
+            rt = self._runtime
+            if rt is not None and rt.lib is not None and self.ptr:
+                rt.lib.cnb_free(self.ptr, rt.stream)
+        except Exception:
+            pass
+        self.ptr = None
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a NumPy array (for asynchronous H2D / D2H)."""
+
+    def __init__(self, runtime: "Runtime", nbytes: int) -> None:
+        self._runtime = runtime
+        self.nbytes = int(nbytes)
+        self.ptr = _lib.check_ptr(runtime.lib.cnb_host_alloc(max(self.nbytes, 1)))
+
+    def as_array(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        buf = (ctypes.c_byte * max(self.nbytes, 1)).from_address(self.ptr)
+        buf._owner = self  # the ctypes buffer (hence every NumPy view of it) keeps the pages alive
+        return np.frombuffer(buf, dtype=np.uint8, count=self.nbytes).view(dtype).reshape(shape)
+
+    def __del__(self) -> None:
+        try:
+            if self.ptr and self._runtime.lib is not None:
+                self._runtime.lib.cnb_host_free(self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
+
+
+class Runtime:
+    def __init__(self) -> None:
+        self.lib: Any = None
+        self.stream: Any = None
+        self.device: int = -1
+        self.rank: int = 0
+        self.world_size: int = 1
+        self.comm: Any = None
+        self._scalar_cache: dict = {}
+        self._argred_uids: dict = {}
+
+    # ------------------------------------------------------------------ lifecycle
+    def ensure_initialized(self) -> None:
+        if self.lib is not None:
+            return
+        lib = _lib.load()
+        ndev = lib.cnb_device_count()
+        if ndev <= 0:
+            raise RuntimeError(
+                "cunumeric_b200: no CUDA device visible. This library runs on B200 (sm_100a) "
+                "only and has no CPU fallback.")
+        device = int(os.environ.get("CUNUMERIC_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device %= ndev
+        _lib.check(lib.cnb_init(device))
+        self.lib = lib
+        self.device = device
+        # reference: cunumeric_perform_registration is the cffi registration callback
+        lib.cunumeric_perform_registration()
+        self.stream = _lib.check_ptr(lib.cnb_stream_create())
+
+    @property
+    def sm_count(self) -> int:
+        self.ensure_initialized()
+        return self.lib.cnb_sm_count()
+
+    def launch_count(self) -> int:
+        self.ensure_initialized()
+        return int(self.lib.cnb_launch_count())
+
+    def synchronize(self) -> None:
+        self.ensure_initialized()
+        _lib.check(self.lib.cnb_stream_synchronize(self.stream))
+
+    # ------------------------------------------------------------------ memory
+    def allocate(self, nbytes: int) -> DeviceBuffer:
+        self.ensure_initialized()
+        return DeviceBuffer(self, nbytes)
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        self.ensure_initialized()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        return PinnedBuffer(self, n).as_array(shape, dtype)
+
+    def copy_h2d(self, dst_ptr: int, src: np.ndarray) -> None:
+        assert src.flags.c_contiguous
+        if src.nbytes:
+            _lib.check(self.lib.cnb_memcpy_h2d(dst_ptr, src.ctypes.data, src.nbytes, self.stream))
+
+    def copy_d2h(self, dst: np.ndarray, src_ptr: int) -> None:
+        assert dst.flags.c_contiguous
+        if dst.nbytes:
+            _lib.check(self.lib.cnb_memcpy_d2h(dst.ctypes.data, src_ptr, dst.nbytes, self.stream))
+
+    def scalar_buffer(self, value: np.ndarray) -> DeviceBuffer:
+        """Device copy of one scalar (the reference's Future-backed 0-d store); small LRU so that
+        constants such as the `0.2` of the stencil are uploaded once."""
+        key = (value.dtype.str, value.tobytes())
+        buf = self._scalar_cache.get(key)
+        if buf is None:
+            if len(self._scalar_cache) > 1024:
+                self._scalar_cache.clear()
+            buf = self.allocate(value.nbytes)
+            staged = np.ascontiguousarray(value)
+            self.copy_h2d(buf.ptr, staged)
+            # the H2D of a pageable source is staged by the driver before returning
+            self._scalar_cache[key] = buf
+        return buf
+
+    # ------------------------------------------------------------------ arg-reduction struct types
+    def get_argred_type(self, elem_dtype) -> np.dtype:
+        """cunumeric/runtime.py:125-134: build {int64, T} and register its Argmax/Argmin redops."""
+        self.ensure_initialized()
+        elem_dtype = np.dtype(elem_dtype)
+        dt = argval_dtype(elem_dtype)
+        if elem_dtype not in self._argred_uids:
+            uid = 1000 + dtype_code(elem_dtype)
+            self.lib.cunumeric_register_reduction_op(uid, dtype_code(elem_dtype))
+            self._argred_uids[elem_dtype] = uid
+        return dt
+
+    # ------------------------------------------------------------------ multi-GPU
+    def init_distributed(self, rank: Optional[int] = None, world_size: Optional[int] = None,
+                         exchange_id=None) -> None:
+        """Create the NCCL clique (one process per GPU). `exchange_id(id_bytes|None) -> id_bytes`
+        broadcasts rank 0's unique id; by default torch.distributed (any backend) is used as the
+        bootstrap plumbing if it is already initialised."""
+        self.ensure_initialized()
+        if rank is None:
+            rank = int(os.environ.get("RANK", "0"))
+        if world_size is None:
+            world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank, self.world_size = rank, world_size
+        if world_size == 1 or self.comm is not None:
+            return
+        ident = ctypes.create_string_buffer(_lib.COMM_ID_BYTES)
+        if rank == 0:
+            _lib.check(self.lib.cnb_comm_unique_id(ident))
+        if exchange_id is None:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RuntimeError("init_distributed needs torch.distributed initialised "
+                                   "(or pass exchange_id=)")
+            obj = [ident.raw if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            raw = obj[0]
+        else:
+            raw = exchange_id(ident.raw if rank == 0 else None)
+        ident = ctypes.create_string_buffer(raw, _lib.COMM_ID_BYTES)
+        self.comm = _lib.check_ptr(self.lib.cnb_comm_init(ident, world_size, rank))
+
+
+runtime = Runtime()

@@ -1,0 +1,90 @@
+"""The reference's example programs that define the benchmark configs, written against the NumPy
+API exactly as the reference ships them (examples/black_scholes.py:23-68, examples/stencil.py:
+23-49) and parameterised on the array module `xp`, so the very same program text runs on
+cunumeric_b200 (the product), on NumPy, and op-by-op on the oracle (oracle/refnp.py)."""
+from __future__ import annotations
+
+import numpy as _np
+
+
+# ------------------------------------------------------------------ Black-Scholes (config C2)
+def black_scholes_inputs(n: int, dtype=_np.float32, seed: int = 0):
+    """examples/black_scholes.py:23-37 on the host: S~U(5,30), X~U(1,100), T~U(0.25,10)."""
+    rng = _np.random.default_rng(seed)
+
+    def generate(lo, hi):
+        diff = dtype(hi) - dtype(lo)
+        r = rng.random(n).astype(dtype)
+        return r * diff + dtype(lo)
+
+    return generate(5, 30), generate(1, 100), generate(0.25, 10)
+
+
+def cnd(d, xp):
+    A1 = 0.31938153
+    A2 = -0.356563782
+    A3 = 1.781477937
+    A4 = -1.821255978
+    A5 = 1.330274429
+    RSQRT2PI = 0.39894228040143267793994605993438
+    K = 1.0 / (1.0 + 0.2316419 * xp.absolute(d))
+    c = RSQRT2PI * xp.exp(-0.5 * d * d) * (K * (A1 + K * (A2 + K * (A3 + K * (A4 + K * A5)))))
+    return xp.where(d > 0, 1.0 - c, c)
+
+
+def black_scholes(S, X, T, R, V, xp=None):
+    """63 elementwise tasks: 7 unary, 28 scalar-operand binary, 24 array-array binary,
+    2 compares, 2 where."""
+    if xp is None:
+        import cunumeric_b200 as xp
+    sqrt_t = xp.sqrt(T)
+    d1 = xp.log(S / X) + (R + 0.5 * V * V) * T / (V * sqrt_t)
+    d2 = d1 - V * sqrt_t
+    cnd_d1 = cnd(d1, xp)
+    cnd_d2 = cnd(d2, xp)
+    exp_rt = xp.exp(-R * T)
+    call_result = S * cnd_d1 - X * exp_rt * cnd_d2
+    put_result = X * exp_rt * (1.0 - cnd_d2) - S * (1.0 - cnd_d1)
+    return call_result, put_result
+
+
+BLACK_SCHOLES_TASKS = 63
+# algorithmic bytes per option, op-by-op: 7 unary x 8 + 2 where x 13 + 2 compare x 5
+# + 28 scalar-operand binary x 8 + 24 array-array binary x 12
+BLACK_SCHOLES_BYTES_PER_OPTION_F32 = 7 * 8 + 2 * 13 + 2 * 5 + 28 * 8 + 24 * 12
+assert BLACK_SCHOLES_BYTES_PER_OPTION_F32 == 604
+
+
+# ------------------------------------------------------------------ 5-point Jacobi (configs C1/C4)
+def stencil_init(N: int, dtype=_np.float64, xp=None):
+    """examples/stencil.py:23-30."""
+    if xp is None:
+        import cunumeric_b200 as xp
+    grid = xp.zeros((N + 2, N + 2), dtype=dtype)
+    grid[:, 0] = -273.15
+    grid[:, -1] = -273.15
+    grid[-1, :] = -273.15
+    grid[0, :] = 40.0
+    return grid
+
+
+def stencil_run(grid, iters: int):
+    """examples/stencil.py:33-50: six tasks per iteration (4 ADD on shifted views, one scalar
+    MULTIPLY, one COPY back into the interior view)."""
+    center = grid[1:-1, 1:-1]
+    north = grid[0:-2, 1:-1]
+    east = grid[1:-1, 2:]
+    west = grid[1:-1, 0:-2]
+    south = grid[2:, 1:-1]
+    work = None
+    for _ in range(iters):
+        average = center + north + east + west + south
+        work = 0.2 * average
+        center[:] = work
+    return work
+
+
+STENCIL_TASKS_PER_ITER = 6
+# per interior point per iteration, op-by-op: 4 ADD x 3 operands + scalar MULTIPLY (2) + COPY (2)
+STENCIL_BYTES_PER_POINT_F64 = (4 * 3 + 2 + 2) * 8
+assert STENCIL_BYTES_PER_POINT_F64 == 128

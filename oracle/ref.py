@@ -81,6 +81,7 @@ def lib():
         vp, i32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
         L.ref_binary_out_code.argtypes = [i32, i32]
         L.ref_binary_op.argtypes = [i32, i32, vp, vp, vp, sz, vp, i32]
+        L.ref_binary_op_strided.argtypes = [i32, i32, vp, sz, vp, sz, vp, sz, vp, i32]
         L.ref_unary_out_code.argtypes = [i32, i32]
         L.ref_unary_op.argtypes = [i32, i32, vp, vp, sz, vp, i32]
         L.ref_unary_multiout.argtypes = [i32, i32, vp, vp, vp, sz]
@@ -99,7 +100,9 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 def _dense(a, dtype=None) -> np.ndarray:
-    return np.ascontiguousarray(a, dtype=dtype)
+    a = np.asarray(a, dtype=dtype)
+    # (np.ascontiguousarray would promote 0-d arrays to shape (1,))
+    return a if a.ndim == 0 else np.ascontiguousarray(a)
 
 
 def _i64(seq: Sequence[int]) -> np.ndarray:
@@ -134,6 +137,26 @@ def binary_op(op: str, a, b, rtol: float = 1e-5, atol: float = 1e-8, nthreads: i
     extra = np.array([rtol, atol], dtype=np.float64)
     rc = lib().ref_binary_op(BINARY[op], CODE_OF[a.dtype], _ptr(a), _ptr(b), _ptr(out), a.size,
                              _ptr(extra), nthreads)
+    assert rc == CODE_OF[odt], rc
+    return out
+
+
+def binary_op_bcast(op: str, a, b, nthreads: int = 1, out=None):
+    """binary_op where either operand may be a 0-d scalar read through a stride-0 accessor (no
+    materialised broadcast) — what the reference's CPU loop does for Future-backed scalars."""
+    a = _dense(a)
+    b = _dense(b, np.int32 if op == "LDEXP" else a.dtype)
+    shape = a.shape if a.ndim else b.shape
+    n = int(np.prod(shape, dtype=np.int64))
+    odt = binary_out_dtype(op, a.dtype)
+    if odt is None:
+        raise InvalidOp(f"{op}/{a.dtype}")
+    if out is None:
+        out = np.empty(shape, dtype=odt)
+    extra = np.array([1e-5, 1e-8], dtype=np.float64)
+    rc = lib().ref_binary_op_strided(BINARY[op], CODE_OF[a.dtype], _ptr(a), 1 if a.ndim else 0,
+                                     _ptr(b), 1 if b.ndim else 0, _ptr(out), n, _ptr(extra),
+                                     nthreads)
     assert rc == CODE_OF[odt], rc
     return out
 

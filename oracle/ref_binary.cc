@@ -11,9 +11,12 @@ using ref::Code;
 
 namespace {
 
+// s1/s2: element strides of the operands (1 = dense, 0 = a promoted scalar read through a
+// stride-0 accessor, the way Future-backed scalar operands reach the reference's generic loop,
+// binary_op.cc:46-49)
 template <BinaryOpCode OP, Code CODE>
 int run(const void* in1v, const void* in2v, void* outv, size_t n, const double* extra, int nthreads,
-        bool query_only)
+        bool query_only, size_t s1 = 1, size_t s2 = 1)
 {
   if constexpr (!BinaryOp<OP, CODE>::valid) {
     return ref::ERR_INVALID;
@@ -34,9 +37,9 @@ int run(const void* in1v, const void* in2v, void* outv, size_t n, const double* 
     auto out = static_cast<LHS*>(outv);
     if (nthreads > 1) {
 #pragma omp parallel for schedule(static) num_threads(nthreads)
-      for (size_t idx = 0; idx < n; ++idx) out[idx] = func(in1[idx], in2[idx]);
+      for (size_t idx = 0; idx < n; ++idx) out[idx] = func(in1[idx * s1], in2[idx * s2]);
     } else {
-      for (size_t idx = 0; idx < n; ++idx) out[idx] = func(in1[idx], in2[idx]);
+      for (size_t idx = 0; idx < n; ++idx) out[idx] = func(in1[idx * s1], in2[idx * s2]);
     }
     return ref::code_of<LHS>::value;
   }
@@ -44,18 +47,19 @@ int run(const void* in1v, const void* in2v, void* outv, size_t n, const double* 
 
 template <BinaryOpCode OP>
 int by_type(int code, const void* a, const void* b, void* o, size_t n, const double* extra,
-            int nthreads, bool q)
+            int nthreads, bool q, size_t s1, size_t s2)
 {
   return ref::type_dispatch(code, [&](auto tag) {
-    return run<OP, decltype(tag)::value>(a, b, o, n, extra, nthreads, q);
+    return run<OP, decltype(tag)::value>(a, b, o, n, extra, nthreads, q, s1, s2);
   });
 }
 
 int dispatch(int op, int code, const void* a, const void* b, void* o, size_t n,
-             const double* extra, int nthreads, bool q)
+             const double* extra, int nthreads, bool q, size_t s1 = 1, size_t s2 = 1)
 {
-#define CASE(NAME) \
-  case BinaryOpCode::NAME: return by_type<BinaryOpCode::NAME>(code, a, b, o, n, extra, nthreads, q);
+#define CASE(NAME)        \
+  case BinaryOpCode::NAME: \
+    return by_type<BinaryOpCode::NAME>(code, a, b, o, n, extra, nthreads, q, s1, s2);
   switch (static_cast<BinaryOpCode>(op)) {
     CASE(ADD) CASE(ARCTAN2) CASE(BITWISE_AND) CASE(BITWISE_OR) CASE(BITWISE_XOR) CASE(COPYSIGN)
     CASE(DIVIDE) CASE(EQUAL) CASE(FLOAT_POWER) CASE(FLOOR_DIVIDE) CASE(FMOD) CASE(GCD)
@@ -83,5 +87,12 @@ int ref_binary_op(int op, int code, const void* in1, const void* in2, void* out,
                   const double* extra, int nthreads)
 {
   return dispatch(op, code, in1, in2, out, n, extra, nthreads, false);
+}
+
+// Same, with per-operand element strides (0 = broadcast scalar operand).
+int ref_binary_op_strided(int op, int code, const void* in1, size_t s1, const void* in2, size_t s2,
+                          void* out, size_t n, const double* extra, int nthreads)
+{
+  return dispatch(op, code, in1, in2, out, n, extra, nthreads, false, s1, s2);
 }
 }

@@ -1,0 +1,220 @@
+"""GPU parity: every (opcode, dtype) pair the reference marks valid, CUDA path (through the C ABI)
+against the oracle (the reference's own functors, oracle/_ref) on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact for integer/boolean results and IEEE add/mul/div/
+compare and the other exactly-rounded ops; <= 2 ulp for transcendentals (written per test)."""
+import numpy as np
+import pytest
+
+from oracle import ref
+
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+N = 10007  # two full vector tiles of the fp32 kernels plus a ragged tail
+TRANSCENDENTAL_ULP = 2
+
+# complex arithmetic beyond add/sub/mul goes through different (equally valid) library algorithms
+# on CPU (libstdc++/glibc) and GPU (libcu++): hold it to a small ulp budget on each component
+COMPLEX_ULP = {"DIVIDE": 4, "POWER": 64, "FLOAT_POWER": 64}
+
+
+def binary_inputs(op, dt, rng):
+    k1 = k2 = "general"
+    if op in ("FLOOR_DIVIDE", "MOD", "FMOD"):
+        k2 = "nonzero"
+    elif op in ("LEFT_SHIFT", "RIGHT_SHIFT"):
+        k1, k2 = "small", "shift"
+    elif op in ("POWER", "FLOAT_POWER"):
+        k1, k2 = "pow_base", "pow_exp"
+    elif op in ("GCD", "LCM"):
+        k1 = k2 = "small"
+    elif op in ("LOGADDEXP", "LOGADDEXP2", "HYPOT", "ARCTAN2"):
+        k1 = k2 = "small"
+    a = pu.make_input(dt, N, rng, k1)
+    if op == "LDEXP":
+        b = rng.integers(-8, 8, N).astype(np.int32)
+    else:
+        b = pu.make_input(dt, N, rng, k2)
+    if op in ("EQUAL", "NOT_EQUAL", "LESS", "LESS_EQUAL", "GREATER", "GREATER_EQUAL", "MAXIMUM",
+              "MINIMUM", "ISCLOSE", "LOGADDEXP", "LOGADDEXP2"):
+        b[::3] = a[::3]  # ties
+    if dt.kind == "f" and op in ("ADD", "SUBTRACT", "MULTIPLY", "DIVIDE", "EQUAL", "LESS",
+                                 "MAXIMUM", "MINIMUM", "COPYSIGN", "ISCLOSE", "LOGICAL_AND"):
+        pu.with_specials(a, rng)
+        pu.with_specials(b, rng)
+    return a, b
+
+
+def binary_tolerance(op, dt, odt):
+    if odt.kind not in "fc":
+        return 0
+    if dt.kind == "c":
+        if op in ("ADD", "SUBTRACT", "MULTIPLY", "MAXIMUM", "MINIMUM"):
+            return 0
+        return COMPLEX_ULP.get(op, TRANSCENDENTAL_ULP)
+    if op in pu.EXACT_BINARY:
+        return 0
+    return TRANSCENDENTAL_ULP
+
+
+@pytest.mark.parametrize("op", ref.BINARY_OPS)
+@pytest.mark.parametrize("dt", pu.DTYPES, ids=lambda d: d.name)
+def test_binary_op(op, dt):
+    odt = ref.binary_out_dtype(op, dt)
+    if odt is None:
+        pytest.skip("reference marks this (op, dtype) invalid")
+    rng = pu.rng_for("binary", op, dt.name)
+    a, b = binary_inputs(op, dt, rng)
+    args = (1e-3, 1e-5) if op == "ISCLOSE" else ()
+    with np.errstate(all="ignore"):
+        exp = ref.binary_op(op, a, b, *args)
+    got = pu.gpu_binary(op, a, b, odt, args)
+    pu.assert_close_ulp(got, exp, binary_tolerance(op, dt, odt), f"{op}/{dt.name}")
+
+
+def test_invalid_binary_pairs_are_rejected():
+    from cunumeric_b200._lib import CnbError
+
+    n = 0
+    for op in ref.BINARY_OPS:
+        for dt in pu.DTYPES:
+            if ref.binary_out_dtype(op, dt) is None:
+                a = np.ones(8, dtype=dt)
+                with pytest.raises(CnbError) as ei:
+                    pu.gpu_binary(op, a, a, dt)
+                assert ei.value.code == -1
+                n += 1
+    assert n == 35 * 14 - 358
+
+
+def unary_inputs(op, dt, rng):
+    kind = "general"
+    if op in ("ARCSIN", "ARCCOS", "ARCTANH"):
+        kind = "unit"
+    elif op in ("LOG", "LOG2", "LOG10", "SQRT"):
+        kind = "positive" if dt.kind != "c" else "small"
+    elif op == "ARCCOSH":
+        kind = "ge1"
+    elif op in ("EXP", "EXP2", "EXPM1", "SINH", "COSH", "TANH", "SIN", "COS", "TAN", "LOG1P",
+                "ARCSINH", "ARCTAN", "CBRT", "SQUARE"):
+        kind = "small"
+    elif op == "RECIPROCAL":
+        kind = "nonzero"
+    a = pu.make_input(dt, N, rng, kind)
+    if op == "LOG1P" and dt.kind == "f":
+        a = np.abs(a)
+    if dt.kind in "fc" and op in ("ISFINITE", "ISINF", "ISNAN", "SIGNBIT", "ABSOLUTE", "NEGATIVE",
+                                  "SIGN", "CEIL", "FLOOR", "TRUNC", "RINT", "LOGICAL_NOT",
+                                  "RECIPROCAL", "COPY", "CONJ"):
+        pu.with_specials(a, rng)
+    if op in ("RINT", "CEIL", "FLOOR", "TRUNC") and dt.kind == "f":
+        a[:64] = (np.arange(64) - 32) * 0.5  # exact .5 ties
+    return a
+
+
+def unary_tolerance(op, dt, odt):
+    if odt.kind not in "fc":
+        return 0
+    if op in pu.EXACT_UNARY and not (dt.kind == "c" and op in ("ABSOLUTE", "SQRT", "RECIPROCAL")):
+        return 0
+    if dt.kind == "c":
+        return 4
+    return TRANSCENDENTAL_ULP
+
+
+UNARY_SINGLE = [o for o in ref.UNARY_OPS if o not in ("FREXP", "MODF", "GETARG")]
+
+
+@pytest.mark.parametrize("op", UNARY_SINGLE)
+@pytest.mark.parametrize("dt", pu.DTYPES, ids=lambda d: d.name)
+def test_unary_op(op, dt):
+    odt = ref.unary_out_dtype(op, dt)
+    if odt is None:
+        pytest.skip("reference marks this (op, dtype) invalid")
+    rng = pu.rng_for("unary", op, dt.name)
+    a = unary_inputs(op, dt, rng)
+    extra = ()
+    if op == "CLIP":
+        lo, hi = (np.array(v).astype(dt) for v in ((False, True) if dt == np.bool_ else (-3, 5) if dt.kind != "u" else (2, 9)))
+        extra = (lo, hi)
+    with np.errstate(all="ignore"):
+        exp = ref.unary_op(op, a, extra=extra if extra else None)
+    got = pu.gpu_unary(op, a, odt, extra)
+    pu.assert_close_ulp(got, exp, unary_tolerance(op, dt, odt), f"{op}/{dt.name}")
+
+
+@pytest.mark.parametrize("op", ["FREXP", "MODF"])
+@pytest.mark.parametrize("dt", pu.FLOAT_DTYPES, ids=lambda d: d.name)
+def test_unary_multiout(op, dt):
+    from cunumeric_b200.config import UnaryOpCode
+
+    rng = pu.rng_for("multiout", op, dt.name)
+    a = pu.with_specials(pu.make_input(dt, N, rng), rng)
+    a = a[np.isfinite(a)]  # frexp's exponent for inf/nan is unspecified
+    e1, e2 = ref.unary_multiout(op, a)
+    o1 = pu.new_thunk(a.shape, e1.dtype)
+    o2 = pu.new_thunk(a.shape, e2.dtype)
+    o1.unary_op(UnaryOpCode[op], pu.to_device(a), True, (), multiout=(o2,))
+    pu.assert_close_ulp(o1.__numpy_array__(), e1, 0, f"{op}/{dt.name} out1")
+    pu.assert_close_ulp(o2.__numpy_array__(), e2, 0, f"{op}/{dt.name} out2")
+
+
+@pytest.mark.parametrize("nan_op", ref.CONVERT_OPS)
+@pytest.mark.parametrize("src", pu.DTYPES, ids=lambda d: d.name)
+def test_convert(nan_op, src):
+    from cunumeric_b200.config import ConvertCode
+
+    if nan_op != "NOOP" and src.kind not in "fc":
+        pytest.skip("NaN-aware CONVERT exists for floating/complex sources only")
+    for dst in pu.DTYPES:
+        if dst == src:
+            continue
+        rng = pu.rng_for("convert", nan_op, src.name, dst.name)
+        # keep values inside the destination's range: out-of-range float->int is UB in the
+        # reference's static_cast
+        kind = "small"
+        a = pu.make_input(src, N, rng, kind)
+        if dst.kind in "ub" and src.kind in "fc":
+            a = np.abs(a.real).astype(src) if src.kind == "f" else (np.abs(a.real) + 1j * a.imag).astype(src)
+        if dst.kind == "u" and src.kind == "i":
+            a = np.abs(a)
+        if src.kind in "fc" and dst.kind in "fc":
+            pu.with_specials(a, rng)
+        if nan_op != "NOOP":
+            a.reshape(-1)[::7] = np.nan
+        with np.errstate(all="ignore"):
+            exp = ref.convert(a, dst, nan_op)
+        out = pu.new_thunk(a.shape, dst)
+        out.convert(pu.to_device(a), nan_op=ConvertCode[nan_op])
+        pu.assert_close_ulp(out.__numpy_array__(), exp, 0, f"CONVERT {nan_op} {src.name}->{dst.name}")
+
+
+@pytest.mark.parametrize("dt", pu.DTYPES, ids=lambda d: d.name)
+def test_where(dt):
+    rng = pu.rng_for("where", dt.name)
+    m = rng.random(N) < 0.5
+    a = pu.make_input(dt, N, rng)
+    b = pu.make_input(dt, N, rng)
+    exp = ref.where(m, a, b)
+    out = pu.new_thunk(a.shape, dt)
+    out.where(pu.to_device(m), pu.to_device(a), pu.to_device(b))
+    got = out.__numpy_array__()
+    assert got.tobytes() == exp.tobytes()
+
+
+def test_getarg_and_fill():
+    from cunumeric_b200.config import UnaryOpCode, argval_dtype
+
+    av = np.zeros(33, dtype=argval_dtype(np.float32))
+    av["arg"] = np.arange(33) * 7 - 5
+    av["arg_value"] = np.linspace(-1, 1, 33)
+    out = pu.new_thunk(av.shape, np.int64)
+    out.unary_op(UnaryOpCode.GETARG, pu.to_device(av), True, ())
+    assert np.array_equal(out.__numpy_array__(), ref.getarg(av))
+    for dt in pu.DTYPES:
+        t = pu.new_thunk((5, 7), dt)
+        v = np.array(3, dtype=dt)
+        t.fill(v)
+        assert np.array_equal(t.__numpy_array__(), np.full((5, 7), v, dtype=dt))

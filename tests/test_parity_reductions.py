@@ -1,0 +1,213 @@
+"""GPU parity for SCALAR_UNARY_RED and UNARY_RED against the oracle.
+
+Bars: bit-exact for integer / boolean / arg-index results and for MAX/MIN; floating-point SUM-like
+results within n*eps (relative to sum |x|), n = reduction length, eps of the accumulation dtype."""
+import numpy as np
+import pytest
+
+from oracle import ref
+
+import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def thunk_reduce(op, a, axis=None, where=None, initial=None, args=None, keepdims=False):
+    """Drive DeferredArray.unary_reduction exactly like ndarray._perform_unary_reduction does."""
+    from cunumeric_b200.config import UnaryRedCode
+
+    code = UnaryRedCode[op]
+    vdt = ref.red_val_dtype(op, a.dtype)
+    res_dt = np.dtype(np.int64) if op in ref.ARG_RED else vdt
+    axes = tuple(range(a.ndim)) if axis is None else (axis % a.ndim,)
+    out_shape = tuple(n for d, n in enumerate(a.shape) if d not in axes)
+    out = pu.new_thunk(out_shape, res_dt)
+    w = None if where is None else pu.to_device(np.broadcast_to(where, a.shape).copy())
+    out.unary_reduction(code, pu.to_device(a), w, axis, axes, keepdims, args, initial)
+    return out.__numpy_array__()
+
+
+def python_prefill(op, dt):
+    """The value the reference's Python layer pre-fills the output with (deferred.py:213-238):
+    finite finfo min/max, not the Legion identity."""
+    from cunumeric_b200.config import UnaryRedCode
+    from cunumeric_b200.deferred import _UNARY_RED_IDENTITIES
+
+    return _UNARY_RED_IDENTITIES[UnaryRedCode[op]](np.dtype(dt))
+
+
+def check_reduction(op, a, got, exp_val, n, what):
+    exp = exp_val["arg"] if op in ref.ARG_RED else exp_val
+    exp = np.asarray(exp).reshape(np.shape(got))
+    if op in ref.ARG_RED:
+        assert got.dtype == np.int64
+        assert np.array_equal(got, exp), f"{what}: {got} vs {exp}"
+        return
+    assert got.dtype == exp.dtype, what
+    if exp.dtype.kind in "biu" or op in ("MAX", "MIN", "NANMAX", "NANMIN"):
+        assert np.array_equal(got, exp, equal_nan=True), f"{what}: {got} vs {exp}"
+        return
+    # floating SUM/PROD-like: |got - exp| <= n * eps * scale
+    acc_dt = a.dtype if a.dtype.kind != "c" else a.real.dtype
+    eps = np.finfo(acc_dt).eps
+    if op in ("PROD", "NANPROD"):
+        scale = np.abs(exp.astype(np.complex128))
+    else:
+        mag = np.abs(np.nan_to_num(a.astype(np.complex128 if a.dtype.kind == "c" else np.float64)))
+        if op in ("SUM_SQUARES", "VARIANCE"):
+            mag = mag ** 2
+        scale = mag.sum()
+    err = np.abs(got.astype(np.complex128) - exp.astype(np.complex128))
+    bound = 2 * n * eps * np.maximum(scale, np.finfo(np.float64).tiny)
+    assert np.all(err <= bound), f"{what}: err {err.max()} > bound {np.min(bound)}"
+
+
+RED_NO_CONTAINS = [o for o in ref.RED_OPS if o != "CONTAINS"]
+
+
+def red_input(op, dt, shape, rng):
+    n = int(np.prod(shape))
+    if op in ("PROD", "NANPROD"):
+        if dt.kind in "iu":
+            a = rng.integers(1, 3, n).astype(dt)
+        elif dt.kind == "b":
+            a = rng.random(n) < 0.999
+        else:
+            a = rng.uniform(0.98, 1.02, n).astype(dt)
+            if dt.kind == "c":
+                a = (rng.uniform(0.98, 1.02, n) * np.exp(1j * rng.uniform(-0.01, 0.01, n))).astype(dt)
+    elif op in ("ALL", "ANY", "COUNT_NONZERO"):
+        a = pu.make_input(dt, n, rng, "small")
+        a.reshape(-1)[rng.random(n) < 0.4] = 0
+    elif dt == np.float16:
+        a = rng.uniform(-1, 1, n).astype(dt)
+    else:
+        a = pu.make_input(dt, n, rng, "small")
+    if op.startswith("NAN") and dt.kind in "fc":
+        a.reshape(-1)[rng.random(n) < 0.1] = np.nan
+    if op in ("ARGMAX", "ARGMIN", "NANARGMAX", "NANARGMIN", "MAX", "MIN") and dt.kind == "f":
+        # tie-free data, as in tests/integration/test_arg_reduce.py
+        pass
+    return a.reshape(shape)
+
+
+@pytest.mark.parametrize("op", ref.RED_OPS)
+@pytest.mark.parametrize("dt", pu.DTYPES, ids=lambda d: d.name)
+def test_scalar_reduction(op, dt):
+    try:
+        ref.red_identity(op, dt)
+    except ref.InvalidOp:
+        pytest.skip("reference marks this (op, dtype) invalid")
+    rng = pu.rng_for("sred", op, dt.name)
+    n = 70001 if dt != np.float16 else 3001
+    a = red_input(op, dt, (n,), rng)
+    args = None
+    extra = None
+    if op == "CONTAINS":
+        extra = a[n // 2]
+        args = (extra,)
+    if op == "VARIANCE":
+        extra = np.array(a.mean() if dt.kind in "fc" else 1).astype(dt)
+        args = (extra,)
+    prefill = python_prefill(op, dt)
+    exp = ref.scalar_unary_red(op, a, extra=extra, initial=prefill)
+    got = thunk_reduce(op, a, args=args)
+    check_reduction(op, a, got, exp, n, f"scalar {op}/{dt.name}")
+
+
+@pytest.mark.parametrize("op", ["SUM", "MAX", "ARGMAX", "ARGMIN", "ALL", "COUNT_NONZERO", "PROD"])
+@pytest.mark.parametrize("shape,axis", [((37, 53), 0), ((37, 53), 1), ((5, 7, 9), 0), ((5, 7, 9), 1),
+                                        ((5, 7, 9), 2), ((3, 4, 5, 6), 2), ((2000, 3), 0),
+                                        ((3, 2000), 1), ((300, 260), 0), ((260, 4100), 1),
+                                        ((1, 50), 0), ((50, 1), 1)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.float16, np.bool_, np.uint8],
+                         ids=lambda d: np.dtype(d).name)
+def test_axis_reduction(op, shape, axis, dt):
+    dt = np.dtype(dt)
+    try:
+        ref.red_identity(op, dt)
+    except ref.InvalidOp:
+        pytest.skip("invalid")
+    rng = pu.rng_for("ared", op, dt.name, shape, axis)
+    a = red_input(op, dt, shape, rng)
+    exp = ref.unary_red(op, a, axis, initial=python_prefill(op, dt))
+    got = thunk_reduce(op, a, axis=axis)
+    check_reduction(op, a, got, exp, shape[axis], f"axis {op}/{dt.name} {shape}@{axis}")
+
+
+@pytest.mark.parametrize("op", RED_NO_CONTAINS)
+@pytest.mark.parametrize("dt", pu.DTYPES, ids=lambda d: d.name)
+def test_axis_reduction_all_pairs(op, dt):
+    try:
+        ref.red_identity(op, dt)
+    except ref.InvalidOp:
+        pytest.skip("invalid")
+    for shape, axis in (((41, 67), 0), ((41, 67), 1)):
+        rng = pu.rng_for("ared-all", op, dt.name, shape, axis)
+        a = red_input(op, dt, shape, rng)
+        exp = ref.unary_red(op, a, axis, initial=python_prefill(op, dt))
+        got = thunk_reduce(op, a, axis=axis)
+        check_reduction(op, a, got, exp, shape[axis], f"axis {op}/{dt.name} {shape}@{axis}")
+
+
+def test_reductions_on_views_and_where():
+    import cunumeric_b200 as cn
+
+    rng = pu.rng_for("redviews")
+    a = rng.normal(size=(64, 96)).astype(np.float64)
+    A = cn.array(a)
+    # transposed input: the kernel mode follows the memory layout
+    for axis in (0, 1):
+        got = A.T.sum(axis=axis).__array__()
+        exp = ref.unary_red("SUM", a.T, axis, initial=0.0)
+        assert np.allclose(got, exp, rtol=1e-13)
+        got = A[3:-5, 2::3].max(axis=axis).__array__()
+        assert np.array_equal(got, a[3:-5, 2::3].max(axis=axis))
+        assert np.array_equal(A[::2].argmax(axis=axis).__array__(), a[::2].argmax(axis=axis))
+    assert int(A[5:, 7:].argmin()) == int(a[5:, 7:].argmin())
+    # where masks (tests/integration/test_reduction.py:154-158)
+    x = cn.array(np.array([[1, 2], [3, 4]]))
+    assert int(x.sum(where=np.array([False, True]))) == 6
+    w = rng.random(a.shape) < 0.5
+    assert np.allclose(A.sum(where=cn.array(w)).__array__(), a.sum(where=w))
+    assert np.allclose(A.sum(axis=0, where=cn.array(w)).__array__(), a.sum(axis=0, where=w))
+    assert np.allclose(A.sum(axis=1, where=cn.array(w)).__array__(), a.sum(axis=1, where=w))
+
+
+def test_arg_reduction_ties_take_first_occurrence():
+    import cunumeric_b200 as cn
+
+    a = np.zeros(100000, dtype=np.float32)
+    a[[17, 4099, 65000]] = 7.0
+    assert int(cn.array(a).argmax()) == 17
+    assert int(ref.scalar_unary_red("ARGMAX", a)["arg"]) == 17
+    b = np.zeros((3000, 5), dtype=np.int32)
+    b[[5, 2500], :] = 9
+    assert np.array_equal(cn.array(b).argmax(axis=0).__array__(), np.full(5, 5))
+
+
+def test_global_index_of_partitioned_rect():
+    """Arg-reductions return GLOBAL flat indices when the rect is a tile of a larger array
+    (unary_red_util.h:342-351): the C ABI takes origin + global shape."""
+    import ctypes
+
+    from cunumeric_b200 import _lib
+    from cunumeric_b200.config import UnaryRedCode, argval_dtype
+    from cunumeric_b200.runtime import runtime
+
+    rng = pu.rng_for("global-index")
+    full = rng.normal(size=(40, 30)).astype(np.float32)
+    lo, hi = 12, 29
+    tile = np.ascontiguousarray(full[lo:hi])
+    exp = ref.scalar_unary_red("ARGMAX", tile, origin=(lo, 0), shape=full.shape)
+    d_in = pu.to_device(tile)
+    out = pu.new_thunk((1,), argval_dtype(np.float32))
+    out.fill(np.array((np.iinfo(np.int64).min, -np.inf), dtype=out.dtype))
+    origin = (ctypes.c_int64 * 2)(lo, 0)
+    gshape = (ctypes.c_int64 * 2)(*full.shape)
+    di, do = d_in.base.descriptor(), out.base.descriptor()
+    _lib.check(runtime.lib.cnb_scalar_unary_red(int(UnaryRedCode.ARGMAX), ctypes.byref(do),
+                                                ctypes.byref(di), None, origin, gshape, None,
+                                                runtime.stream))
+    got = out.__numpy_array__()[0]
+    assert int(got["arg"]) == int(exp["arg"]) == lo * 30 + int(np.argmax(tile))

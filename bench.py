@@ -18,9 +18,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +34,7 @@ UNIT = "options/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="own", choices=["own", "reference"])
     p.add_argument("--workload", default="black_scholes", choices=["black_scholes", "stencil"])
@@ -61,61 +59,81 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md recipe).
+    Uses NVML in a background thread (same counters as the recipe's nvidia-smi line, without
+    spawning a process that contends for the driver lock while kernels are being launched)."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, device: int) -> None:
+    def __init__(self, device: int, period_s: float = 0.02) -> None:
         self.device = device
-        self.proc = None
-        self.tmp = None
+        self.period = period_s
+        self.samples = []
+        self._stop = None
+        self._thread = None
+        self._err = None
+
+    def _uuid_index(self, nv):
+        # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ent = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.device < len(ent):
+                e = ent[self.device]
+                if e.isdigit():
+                    return int(e)
+                for i in range(nv.nvmlDeviceGetCount()):
+                    h = nv.nvmlDeviceGetHandleByIndex(i)
+                    if nv.nvmlDeviceGetUUID(h).startswith(e):
+                        return i
+        return self.device
 
     def start(self) -> None:
+        import threading
+
         try:
-            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.device)], stdout=self.tmp, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._uuid_index(nv))
+            self._max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception as exc:
+            self._err = f"nvml unavailable: {exc}"
+            return
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    self.samples.append((sm, reasons, power))
+                except Exception as exc:  # keep sampling errors out of the measurement
+                    self._err = str(exc)
+                self._stop.wait(self.period)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.tmp.flush()
-        self.tmp.seek(0)
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.tmp.read().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.tmp.name)
-        except OSError:
-            pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load": the upper half of the samples (idle samples before/after drag the median)
-        loaded = sorted(sm)[len(sm) // 2:]
-        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(smax),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self._err or "not started"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        import pynvml as nv
+
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self._max, "reasons": [self._err or "no samples"]}
+        names = {
+            "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+            "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+            "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+            "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+            "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown,
+        }
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r, _ in self.samples))
+        sm = [s for s, _, _ in self.samples]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self._max, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(p for _, _, p in self.samples)}
 
 
 def dist_setup(world: int):
@@ -276,10 +294,9 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
     # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides
     ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
     sampler = ClockSampler(cn.runtime.device)
-    sampler.start()
-    time.sleep(0.3)
     _lib.check(lib.cnb_trace_start(args.steps * (BLACK_SCHOLES_TASKS + 8)))
     barrier(dist)
+    sampler.start()
     cn.synchronize()
     launches0 = cn.runtime.launch_count()
     lib.cnb_event_record(ev0, cn.runtime.stream)

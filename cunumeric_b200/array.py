@@ -13,6 +13,7 @@ import numpy as np
 
 from .config import ConvertCode, UnaryOpCode, UnaryRedCode, is_supported_dtype
 from .deferred import DeferredArray
+from .distributed import create_empty_thunk, thunk_from_numpy
 from .store import Store
 
 
@@ -43,8 +44,9 @@ def convert_to_cunumeric_ndarray(obj: Any, share: bool = False) -> "ndarray":
     if host.dtype == object or not is_supported_dtype(host.dtype):
         raise TypeError(f"cunumeric_b200 does not support dtype={host.dtype}")
     if host.ndim == 0:
-        return ndarray(shape=(), dtype=host.dtype, thunk=DeferredArray(Store.from_scalar(host)))
-    return ndarray(shape=host.shape, dtype=host.dtype, thunk=DeferredArray.from_numpy(host))
+        return ndarray(shape=(), dtype=host.dtype,
+                       thunk=DeferredArray(Store.from_scalar(host), host_scalar=host))
+    return ndarray(shape=host.shape, dtype=host.dtype, thunk=thunk_from_numpy(host))
 
 
 def broadcast_where(where, shape):
@@ -73,7 +75,7 @@ class ndarray:
                 raise TypeError(f"cunumeric_b200 does not support dtype={dtype}")
             if isinstance(shape, (int, np.integer)):
                 shape = (int(shape),)
-            thunk = DeferredArray(Store.empty(tuple(shape), dtype))
+            thunk = create_empty_thunk(tuple(shape), dtype, inputs)
         self._thunk = thunk
         self._writeback: Optional[np.ndarray] = None
 
@@ -219,7 +221,7 @@ class ndarray:
         return self.reshape(-1).copy()
 
     def copy(self, order="C") -> "ndarray":
-        out = ndarray(self.shape, self.dtype)
+        out = ndarray(self.shape, self.dtype, inputs=(self,))
         out._thunk.copy(self._thunk, deep=True)
         return out
 
@@ -250,6 +252,9 @@ class ndarray:
         dtype = np.dtype(dtype)
         if self.dtype == dtype:
             return self
+        if self._thunk.host_scalar is not None:
+            with np.errstate(all="ignore"):
+                return convert_to_cunumeric_ndarray(self._thunk.host_scalar.astype(dtype))
         result = ndarray(self.shape, dtype=dtype, inputs=(self,))
         result._thunk.convert(self._thunk, warn=False, temporary=temporary)
         return result
@@ -257,6 +262,8 @@ class ndarray:
     def _maybe_convert(self, dtype, hints=None) -> "ndarray":
         if self.dtype == dtype:
             return self
+        if self._thunk.host_scalar is not None:
+            return self._astype(dtype)
         copy = ndarray(shape=self.shape, dtype=dtype, inputs=hints)
         copy._thunk.convert(self._thunk)
         return copy

@@ -1,0 +1,73 @@
+"""Stencil leg of bench.py (BASELINE.json configs[3]): examples/stencil.py fp64, N x N interior,
+row-partitioned over the GPUs, halo rows exchanged over NVLink (NCCL send/recv, stream-ordered).
+Strong scaling: the global grid is fixed, each rank owns (N+2)/world rows."""
+from __future__ import annotations
+
+import ctypes
+import json
+import time
+
+import numpy as np
+
+
+def run_stencil(args, rank, world, dist, ClockSampler, load_peaks, max_over_ranks, barrier) -> None:
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import _lib
+    from cunumeric_b200.partition import RowPartition, halo_bytes
+    from cunumeric_b200.workloads import (STENCIL_BYTES_PER_POINT_F64, STENCIL_TASKS_PER_ITER,
+                                          stencil_init, stencil_run)
+
+    n, iters = args.stencil_n, args.stencil_iters
+    cn.runtime.ensure_initialized()
+    if world > 1:
+        cn.runtime.init_distributed(rank, world)
+    lib = cn.runtime.lib
+    peak_gbs, peak_src = load_peaks()
+    grid = stencil_init(n, np.float64)
+    for _ in range(max(args.warmup, 3)):
+        stencil_run(grid, iters)
+    cn.synchronize()
+
+    ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
+    sampler = ClockSampler(cn.runtime.device)
+    barrier(dist)
+    sampler.start()
+    cn.synchronize()
+    launches0 = cn.runtime.launch_count()
+    lib.cnb_event_record(ev0, cn.runtime.stream)
+    for _ in range(args.steps):
+        stencil_run(grid, iters)
+    lib.cnb_event_record(ev1, cn.runtime.stream)
+    cn.synchronize()
+    barrier(dist)
+    launches = cn.runtime.launch_count() - launches0
+    ms = ctypes.c_float()
+    _lib.check(lib.cnb_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+    clocks = sampler.stop()
+    elapsed = max_over_ranks(dist, ms.value * 1e-3)
+    points = float(n) * n * iters * args.steps
+    value = points / elapsed
+    gbs_per_gpu = value * STENCIL_BYTES_PER_POINT_F64 / 1e9 / world
+    part = RowPartition.even(n + 2, world)
+    sent, recv = halo_bytes(part, 1, (n + 2) * 8, min(1, world - 1))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "stencil_points_per_second", "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"stencil fp64 N={n} (examples/stencil.py), {iters} Jacobi "
+                                   f"iterations per step, {STENCIL_TASKS_PER_ITER} tasks per "
+                                   "iteration issued op-by-op, rows partitioned over the GPUs",
+                       "N": n, "iters_per_step": iters,
+                       "algorithmic_bytes_per_point": STENCIL_BYTES_PER_POINT_F64,
+                       "halo_bytes_per_iter_per_gpu": {"sent": sent, "received": recv},
+                       "l2_policy": f"grid {(n + 2) ** 2 * 8 / 1e9:.1f} GB and temporaries exceed "
+                                    "the 126 MB L2" if n >= 8000 else "working set fits L2"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": gbs_per_gpu, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": gbs_per_gpu / peak_gbs, "traffic": None,
+                         "kernel": "whole iteration (4 ADD on pitched views + scalar MULTIPLY + "
+                                   "COPY), per GPU", "peak_source": peak_src},
+            "cpu_baseline": None, "e2e": None,
+        }))

@@ -68,7 +68,7 @@ def argval_dtype(elem) -> np.dtype:
     builds in the reference (cunumeric/runtime.py:125-134) for Argval<T> (src/cunumeric/arg.h)."""
     elem = np.dtype(elem)
     return np.dtype({"names": ["arg", "arg_value"], "formats": [np.int64, elem],
-                     "offsets": [0, 8], "itemsize": 16})
+                     "offsets": [0, 8], "itemsize": 8 + max(8, elem.itemsize)})
 
 
 def dtype_code(dtype) -> int:

@@ -414,6 +414,20 @@ struct Ldexp {
   }
 };
 
+// a**b for integer-valued a and integer b, in double
+__device__ __forceinline__ double pow_integral(double a, long long b)
+{
+  unsigned long long e = b < 0 ? 0ull - static_cast<unsigned long long>(b)
+                               : static_cast<unsigned long long>(b);
+  double r = 1.0, base = a;
+  while (e != 0) {
+    if (e & 1ull) r *= base;
+    e >>= 1;
+    if (e != 0) base *= base;
+  }
+  return b < 0 ? 1.0 / r : r;
+}
+
 // ---- POWER (:826-861): everything but fp16/complex goes through double ------------------------
 template <typename T>
 struct Power : Base<T> {
@@ -425,6 +439,11 @@ struct Power : Base<T> {
       return f2h(powf(h2f(a), h2f(b)));
     else if constexpr (is_complex_v<T>)
       return cuda::std::pow(a, b);
+    else if constexpr (std::is_integral<T>::value)
+      // integer operands: the reference's pow(double, double) is exact whenever the result is
+      // representable (glibc pow is < 1 ulp), and the cast truncates — a 2-ulp device pow() would
+      // turn 3**3 into 26.  Exponentiation by squaring in double is exact below 2**53.
+      return static_cast<T>(pow_integral(static_cast<double>(a), static_cast<long long>(b)));
     else
       return static_cast<T>(pow(static_cast<double>(a), static_cast<double>(b)));
   }

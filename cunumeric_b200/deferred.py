@@ -75,11 +75,46 @@ def _vp(arr: Optional[np.ndarray]):
     return None if arr is None else arr.ctypes.data_as(ctypes.c_void_p)
 
 
-class DeferredArray:
-    __slots__ = ("base",)
+def _rep(thunk):
+    """Operand of a replicated task: a partitioned thunk (distributed.PartitionedArray) is gathered
+    onto every rank first (collective)."""
+    gather = getattr(thunk, "gather", None)
+    return thunk if gather is None else gather()
 
-    def __init__(self, base: Store) -> None:
+
+def launch_scalar_red(op, out: Store, src: Store, where: Optional[Store], origin, gshape,
+                      args) -> None:
+    """SCALAR_UNARY_RED through the C ABI: folds `src` into the 1-element store `out`.  origin /
+    gshape place the rect in the global array (arg-reductions return global flat indices)."""
+    lhs = out
+    while lhs.ndim > 1:
+        lhs = lhs.project(0, 0)
+    if lhs.ndim == 0:
+        lhs = lhs.promote(0, 1)
+    d_out, d_in = lhs.descriptor(), src.descriptor()
+    d_w = None if where is None else where.descriptor()
+    nd = max(src.ndim, 1)
+    c_origin = c_shape = None
+    if origin is not None:
+        c_origin = (ctypes.c_int64 * nd)(*[int(v) for v in origin])
+        c_shape = (ctypes.c_int64 * nd)(*[int(v) for v in gshape])
+    extra = _host_scalars(args, src.dtype) if args else None
+    _lib.check(runtime.lib.cnb_scalar_unary_red(
+        int(op), ctypes.byref(d_out), ctypes.byref(d_in),
+        None if d_w is None else ctypes.byref(d_w), c_origin, c_shape, _vp(extra),
+        runtime.stream))
+
+
+class DeferredArray:
+    __slots__ = ("base", "host_scalar")
+
+    def __init__(self, base: Store, host_scalar: Optional[np.ndarray] = None) -> None:
         self.base = base
+        # 0-d operands that came from the host (Python / NumPy scalars) keep their host value, so
+        # dtype conversions of scalars happen on the host — the counterpart of the reference
+        # routing tiny arrays through its eager NumPy thunk (runtime.py:448-500) instead of
+        # launching a one-element CONVERT task.
+        self.host_scalar = host_scalar
 
     # ------------------------------------------------------------------ basic properties
     @property
@@ -147,7 +182,7 @@ class DeferredArray:
                  args: Sequence[Any] = (), multiout: Optional[Sequence["DeferredArray"]] = None
                  ) -> None:
         lhs = self.base
-        src = self._copy_if_overlapping(src)
+        src = self._copy_if_overlapping(_rep(src))
         rhs = src._broadcast(lhs.shape)
         out2 = None
         if multiout:
@@ -164,8 +199,8 @@ class DeferredArray:
     def binary_op(self, op_code: BinaryOpCode, src1: "DeferredArray", src2: "DeferredArray",
                   where: Any = True, args: Sequence[Any] = ()) -> None:
         lhs = self.base
-        src1 = self._copy_if_overlapping(src1)
-        src2 = self._copy_if_overlapping(src2)
+        src1 = self._copy_if_overlapping(_rep(src1))
+        src2 = self._copy_if_overlapping(_rep(src2))
         rhs1 = src1._broadcast(lhs.shape)
         rhs2 = src2._broadcast(lhs.shape)
         extra = _host_scalars(args, np.float64) if op_code == BinaryOpCode.ISCLOSE else None
@@ -180,9 +215,9 @@ class DeferredArray:
     # ------------------------------------------------------------------ WHERE
     def where(self, mask: "DeferredArray", one: "DeferredArray", two: "DeferredArray") -> None:
         lhs = self.base
-        m = self._copy_if_overlapping(mask)._broadcast(lhs.shape)
-        a = self._copy_if_overlapping(one)._broadcast(lhs.shape)
-        b = self._copy_if_overlapping(two)._broadcast(lhs.shape)
+        m = self._copy_if_overlapping(_rep(mask))._broadcast(lhs.shape)
+        a = self._copy_if_overlapping(_rep(one))._broadcast(lhs.shape)
+        b = self._copy_if_overlapping(_rep(two))._broadcast(lhs.shape)
         d_out, dm, da, db = lhs.descriptor(), m.descriptor(), a.descriptor(), b.descriptor()
         _lib.check(runtime.lib.cnb_where(ctypes.byref(d_out), ctypes.byref(dm), ctypes.byref(da),
                                          ctypes.byref(db), runtime.stream))
@@ -191,6 +226,7 @@ class DeferredArray:
     def convert(self, rhs: "DeferredArray", warn: bool = True,
                 nan_op: ConvertCode = ConvertCode.NOOP, temporary: bool = False) -> None:
         lhs = self.base
+        rhs = _rep(rhs)
         if rhs.dtype == lhs.dtype:
             self.copy(rhs, deep=True)
             return
@@ -203,6 +239,7 @@ class DeferredArray:
     # ------------------------------------------------------------------ COPY / FILL
     def copy(self, rhs: "DeferredArray", deep: bool = False) -> None:
         """deferred.py:392-401: UNARY_OP(COPY) from rhs into this window."""
+        rhs = _rep(rhs)
         if self.base.same_window(rhs.base):
             return
         self.unary_op(UnaryOpCode.COPY, rhs, True, ())
@@ -219,6 +256,10 @@ class DeferredArray:
                         axes: Optional[Sequence[int]], keepdims: bool, args: Any,
                         initial: Any) -> None:
         """deferred.py:3170-3288.  `self` is the (pre-existing) result thunk."""
+        if hasattr(src, "reduce_into"):  # row-partitioned source: local partial + NCCL combine
+            src.reduce_into(self, op, where, orig_axis, axes, keepdims, args, initial)
+            return
+        where = None if where is None else _rep(where)
         lhs_array = self
         rhs_array = src
         argred = op in _ARG_REDS
@@ -244,13 +285,9 @@ class DeferredArray:
                 lhs = lhs.project(0, 0)
             if lhs.ndim == 0:
                 lhs = lhs.promote(0, 1)
-            d_out = lhs.descriptor()
-            extra = None
-            if args:
-                extra = _host_scalars(args, rhs_array.dtype)
-            _lib.check(runtime.lib.cnb_scalar_unary_red(
-                int(op), ctypes.byref(d_out), ctypes.byref(d_in), p_where, None, None,
-                _vp(extra), runtime.stream))
+            launch_scalar_red(op, lhs, rhs_array.base,
+                              None if where is None else where._broadcast(rhs_array.shape),
+                              None, None, args)
         else:
             assert axes is not None
             if len(axes) > 1:

@@ -1,0 +1,608 @@
+"""PartitionedArray: the multi-GPU thunk (one process per GPU, SPMD).
+
+In the reference every thunk is a DeferredArray and legate.core tiles its store over the GPUs
+(SURVEY §2.2).  Here the tiling is explicit: a PartitionedArray owns a contiguous block of rows of
+the global array (plus `halo` ghost rows on each side) in a local DeferredArray, and implements the
+same thunk surface — unary_op / binary_op / where / convert / copy / fill / unary_reduction /
+get_item / set_item — by running the single-GPU task on the local block.  The exchange steps Legion
+performs implicitly are explicit, stream-ordered NCCL calls over NVLink:
+  * shifted-slice operands (the stencil's north/south views): one grouped send/recv halo refresh per
+    producer->consumer step (partition.plan_halo), re-done only after the base array was written;
+  * scalar reductions: local partial -> ncclAllReduce (arg-reductions: max/min of the values, then
+    min of the candidate indices, which is the lowest-index tie-break of the sequential fold);
+  * axis-0 reductions (the partitioned axis): full-width local partial -> ncclAllReduce;
+    reductions along other axes need no communication.
+Everything the partition logic decides is a pure function of replicated metadata
+(cunumeric_b200/partition.py), so all ranks issue the same collectives in the same order."""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .config import BinaryOpCode, ConvertCode, UnaryOpCode, UnaryRedCode, dtype_code
+from .deferred import (_ARG_REDS, _UNARY_RED_IDENTITIES, DeferredArray, _basic_index,
+                       launch_scalar_red)
+from .partition import RowPartition, plan_fetch, plan_halo
+from .runtime import runtime
+from .store import Store
+
+DEFAULT_HALO = 1
+
+# how per-rank partials of each reduction are combined across ranks
+_COMBINE = {
+    UnaryRedCode.SUM: UnaryRedCode.SUM, UnaryRedCode.NANSUM: UnaryRedCode.SUM,
+    UnaryRedCode.SUM_SQUARES: UnaryRedCode.SUM, UnaryRedCode.VARIANCE: UnaryRedCode.SUM,
+    UnaryRedCode.COUNT_NONZERO: UnaryRedCode.SUM,
+    UnaryRedCode.PROD: UnaryRedCode.PROD, UnaryRedCode.NANPROD: UnaryRedCode.PROD,
+    UnaryRedCode.MAX: UnaryRedCode.MAX, UnaryRedCode.NANMAX: UnaryRedCode.MAX,
+    UnaryRedCode.MIN: UnaryRedCode.MIN, UnaryRedCode.NANMIN: UnaryRedCode.MIN,
+    UnaryRedCode.ALL: UnaryRedCode.ALL, UnaryRedCode.ANY: UnaryRedCode.ANY,
+    UnaryRedCode.CONTAINS: UnaryRedCode.ANY,
+}
+# ... and the elementwise op that folds a combined partial into a pre-filled output
+_FOLD_BINOP = {
+    UnaryRedCode.SUM: BinaryOpCode.ADD, UnaryRedCode.PROD: BinaryOpCode.MULTIPLY,
+    UnaryRedCode.MAX: BinaryOpCode.MAXIMUM, UnaryRedCode.MIN: BinaryOpCode.MINIMUM,
+    UnaryRedCode.ALL: BinaryOpCode.LOGICAL_AND, UnaryRedCode.ANY: BinaryOpCode.LOGICAL_OR,
+}
+
+
+class _Shared:
+    """State shared by a base array and all of its views."""
+
+    __slots__ = ("gshape", "dtype", "part", "halo", "local", "ghost_valid")
+
+    def __init__(self, gshape, dtype, part: RowPartition, halo: int) -> None:
+        self.gshape = tuple(int(s) for s in gshape)
+        self.dtype = np.dtype(dtype)
+        self.part = part
+        self.halo = int(halo)
+        rows = part.count(runtime.rank) + 2 * self.halo
+        self.local = DeferredArray(Store.empty((rows,) + self.gshape[1:], self.dtype))
+        self.ghost_valid = False
+
+    @property
+    def row_bytes(self) -> int:
+        return int(np.prod(self.gshape[1:], dtype=np.int64)) * self.dtype.itemsize
+
+
+def _comm_check(rc: int) -> None:
+    _lib.check(rc)
+
+
+class PartitionedArray:
+    __slots__ = ("meta", "row0", "row1", "inner_key", "host_scalar")
+
+    def __init__(self, meta: _Shared, row0: int = 0, row1: Optional[int] = None,
+                 inner_key: Tuple = ()) -> None:
+        self.meta = meta
+        self.row0 = row0
+        self.row1 = meta.gshape[0] if row1 is None else row1
+        self.inner_key = inner_key  # basic index applied to dims >= 1 of the local block
+        self.host_scalar = None
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def empty(shape, dtype, like: Optional["PartitionedArray"] = None,
+              halo: int = DEFAULT_HALO) -> "PartitionedArray":
+        shape = tuple(int(s) for s in shape)
+        if like is not None and like.shape[0] == shape[0]:
+            part = like.part  # aligned with the operand it will be computed from
+        else:
+            part = RowPartition.even(shape[0], runtime.world_size)
+        return PartitionedArray(_Shared(shape, dtype, part, halo))
+
+    @staticmethod
+    def from_numpy(array: np.ndarray, halo: int = DEFAULT_HALO) -> "PartitionedArray":
+        """Every rank holds the same host array (SPMD) and uploads only its own rows."""
+        out = PartitionedArray.empty(array.shape, array.dtype, halo=halo)
+        lo, hi = out.part.bounds(runtime.rank)
+        if hi > lo:
+            src = np.ascontiguousarray(array[lo:hi])
+            runtime.copy_h2d(out.local_rows(lo, hi).base.ptr, src)
+        return out
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def part(self) -> RowPartition:
+        """Partition of THIS view's rows (view coordinates)."""
+        return self.meta.part.window(self.row0, self.row1)
+
+    @property
+    def owned(self) -> Tuple[int, int]:
+        return self.part.bounds(runtime.rank)
+
+    @property
+    def shape(self) -> Tuple[int, ...]:
+        probe = Store(None, self.meta.dtype, (self.row1 - self.row0,) + self.meta.gshape[1:])
+        return _basic_index(probe, (slice(None),) + self.inner_key).shape if self.inner_key \
+            else probe.shape
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def dtype(self) -> np.dtype:
+        return self.meta.dtype
+
+    @property
+    def scalar(self) -> bool:
+        return False
+
+    # ------------------------------------------------------------------ local access
+    def local_rows(self, vlo: int, vhi: int) -> DeferredArray:
+        """DeferredArray over view rows [vlo, vhi) (must lie inside owned +- halo)."""
+        m = self.meta
+        lo, hi = m.part.bounds(runtime.rank)
+        b0, b1 = self.row0 + vlo, self.row0 + vhi
+        assert lo - m.halo <= b0 and b1 <= hi + m.halo, (b0, b1, lo, hi, m.halo)
+        base = m.local.base.slice(0, slice(b0 - (lo - m.halo), b1 - (lo - m.halo)))
+        if self.inner_key:
+            base = _basic_index(base, (slice(None),) + self.inner_key)
+        return DeferredArray(base)
+
+    def _invalidate(self) -> None:
+        self.meta.ghost_valid = False
+
+    # ------------------------------------------------------------------ exchange
+    def _run_transfers(self, transfers, dst_base_row0: int, dst: DeferredArray) -> None:
+        """Execute a transfer plan in one NCCL group: sends read this rank's block, receives land
+        in `dst` (a row-contiguous local buffer whose row 0 is base row `dst_base_row0`)."""
+        m = self.meta
+        lib, comm, stream = runtime.lib, runtime.comm, runtime.stream
+        lo, _ = m.part.bounds(runtime.rank)
+        rb = m.row_bytes
+        mine = [t for t in transfers if t.src == runtime.rank or t.dst == runtime.rank]
+        if not mine:
+            return
+        _comm_check(lib.cnb_comm_group_start())
+        for t in mine:
+            if t.src == runtime.rank:
+                ptr = m.local.base.ptr + (t.row_lo - (lo - m.halo)) * rb
+                _comm_check(lib.cnb_comm_send(comm, ptr, t.nrows * rb, t.dst, stream))
+            else:
+                ptr = dst.base.ptr + (t.row_lo - dst_base_row0) * rb
+                _comm_check(lib.cnb_comm_recv(comm, ptr, t.nrows * rb, t.src, stream))
+        _comm_check(lib.cnb_comm_group_end())
+
+    def exchange_halo(self) -> None:
+        """Refresh the ghost rows of the base array from the neighbouring ranks."""
+        m = self.meta
+        if m.ghost_valid or runtime.world_size == 1 or m.halo == 0:
+            m.ghost_valid = True
+            return
+        lo, _ = m.part.bounds(runtime.rank)
+        self._run_transfers(plan_halo(m.part, m.halo), lo - m.halo, m.local)
+        m.ghost_valid = True
+
+    def _ensure_rows(self, needs: Sequence[Tuple[int, int]]) -> None:
+        """`needs[r]` = BASE rows rank r is about to read.  Collective."""
+        m = self.meta
+        within_owned = within_halo = True
+        for r, (nlo, nhi) in enumerate(needs):
+            if nhi <= nlo:
+                continue
+            lo, hi = m.part.bounds(r)
+            if nlo < lo or nhi > hi:
+                within_owned = False
+            if nlo < lo - m.halo or nhi > hi + m.halo:
+                within_halo = False
+        if within_owned:
+            return
+        if within_halo:
+            self.exchange_halo()
+            return
+        raise NotImplementedError(
+            "operand rows are farther than the halo depth from their owner: general "
+            "redistribution is not implemented (use gather() / a larger halo)")
+
+    def gather(self) -> DeferredArray:
+        """Replicated copy of the whole view on every rank (collective)."""
+        m = self.meta
+        n = m.gshape[0]
+        full = DeferredArray(Store.empty(m.gshape, m.dtype))
+        lo, hi = m.part.bounds(runtime.rank)
+        if hi > lo:
+            DeferredArray(full.base.slice(0, slice(lo, hi))).copy(
+                PartitionedArray(m).local_rows(lo, hi), deep=True)
+        if runtime.world_size > 1:
+            self._run_transfers(plan_fetch(m.part, [(0, n)] * runtime.world_size), 0, full)
+        view = full.base.slice(0, slice(self.row0, self.row1))
+        if self.inner_key:
+            view = _basic_index(view, (slice(None),) + self.inner_key)
+        return DeferredArray(view)
+
+    def __numpy_array__(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        return self.gather().__numpy_array__(out)
+
+    # ------------------------------------------------------------------ operand alignment
+    def _operand(self, src: Any, vlo: int, vhi: int) -> DeferredArray:
+        """Local piece of `src` aligned with this (output) view's rows [vlo, vhi)."""
+        if isinstance(src, PartitionedArray):
+            if src.ndim != self.ndim:
+                raise NotImplementedError("partitioned operands must have the output's rank")
+            if src.shape[0] != self.shape[0]:
+                raise NotImplementedError("broadcasting a partitioned operand along axis 0")
+            mine = self.part
+            needs = []
+            for r in range(runtime.world_size):
+                a, b = mine.bounds(r)
+                needs.append((src.row0 + a, src.row0 + b))
+            src._ensure_rows(needs)
+            return src.local_rows(vlo, vhi)
+        # replicated operand: scalars and lower-rank / unit-row arrays broadcast, full-height ones
+        # are cut to the local rows
+        if src.ndim == self.ndim and self.ndim > 0 and src.shape[0] == self.shape[0] \
+                and self.shape[0] != 1:
+            return DeferredArray(src.base.slice(0, slice(vlo, vhi)))
+        return src
+
+    def _local_task(self, fn, srcs: Sequence[Any]) -> None:
+        vlo, vhi = self.owned
+        local_srcs = [self._operand(s, vlo, vhi) for s in srcs]  # collective part first
+        if vhi > vlo:
+            fn(self.local_rows(vlo, vhi), *local_srcs)
+        self._invalidate()
+
+    # ------------------------------------------------------------------ thunk surface
+    def unary_op(self, op, src, where=True, args=(), multiout=None) -> None:
+        if multiout:
+            vlo, vhi = self.owned
+            outs = [o.local_rows(*o.owned) for o in multiout]
+            self._local_task(lambda out, s: out.unary_op(op, s, where, args, multiout=outs), [src])
+            for o in multiout:
+                o._invalidate()
+            return
+        self._local_task(lambda out, s: out.unary_op(op, s, where, args), [src])
+
+    def binary_op(self, op_code, src1, src2, where=True, args=()) -> None:
+        self._local_task(lambda out, a, b: out.binary_op(op_code, a, b, where, args), [src1, src2])
+
+    def isclose(self, rhs1, rhs2, rtol, atol, equal_nan) -> None:
+        assert not equal_nan
+        self.binary_op(BinaryOpCode.ISCLOSE, rhs1, rhs2, True, (rtol, atol))
+
+    def where(self, mask, one, two) -> None:
+        self._local_task(lambda out, m, a, b: out.where(m, a, b), [mask, one, two])
+
+    def convert(self, rhs, warn=True, nan_op=ConvertCode.NOOP, temporary=False) -> None:
+        self._local_task(lambda out, s: out.convert(s, warn, nan_op, temporary), [rhs])
+
+    def copy(self, rhs, deep=False) -> None:
+        self._local_task(lambda out, s: out.copy(s, deep), [rhs])
+
+    def fill(self, value) -> None:
+        vlo, vhi = self.owned
+        if vhi > vlo:
+            self.local_rows(vlo, vhi).fill(value)
+        self._invalidate()
+
+    def _broadcast(self, shape):
+        raise NotImplementedError("a partitioned array cannot be the source of a replicated task; "
+                                  "gather() it first")
+
+    # ------------------------------------------------------------------ views
+    def get_item(self, key: Any) -> Any:
+        if not isinstance(key, tuple):
+            key = (key,)
+        k0 = key[0] if key else slice(None)
+        rest = tuple(key[1:])
+        if k0 is Ellipsis:
+            k0, rest = slice(None), (Ellipsis,) + rest
+        if self.inner_key:
+            # a view of a view: only further ROW slicing is supported
+            if any(not (k is Ellipsis or k == slice(None)) for k in rest):
+                raise NotImplementedError("column indexing of an already column-sliced "
+                                          "partitioned view")
+            rest = self.inner_key
+        n = self.row1 - self.row0
+        if isinstance(k0, slice):
+            start, stop, step = k0.indices(n)
+            if step != 1:
+                raise NotImplementedError("stepped slices along the partitioned axis")
+            stop = max(stop, start)
+            return PartitionedArray(self.meta, self.row0 + start, self.row0 + stop, rest)
+        if isinstance(k0, (int, np.integer)):
+            # a single row: a view that only its owner holds
+            idx = int(k0) + (n if int(k0) < 0 else 0)
+            if not (0 <= idx < n):
+                raise IndexError(f"index {int(k0)} is out of bounds for axis 0 with size {n}")
+            return _RowView(self.meta, self.row0 + idx, rest)
+        raise NotImplementedError("only basic indexing is supported on partitioned arrays")
+
+    def set_item(self, key: Any, rhs: Any) -> None:
+        view = self.get_item(key)
+        if isinstance(view, _RowView):
+            view.assign(rhs)
+            return
+        if isinstance(rhs, DeferredArray) and rhs.dtype != view.dtype:
+            tmp = DeferredArray(Store.empty(rhs.shape, view.dtype))
+            tmp.convert(rhs)
+            rhs = tmp
+        elif isinstance(rhs, PartitionedArray) and rhs.dtype != view.dtype:
+            tmp = PartitionedArray.empty(rhs.shape, view.dtype, like=rhs)
+            tmp.convert(rhs)
+            rhs = tmp
+        view.copy(rhs, deep=False)
+
+    def transpose(self, axes):
+        if tuple(axes) == tuple(range(self.ndim)):
+            return self
+        raise NotImplementedError("transposing a partitioned array needs an all-to-all; gather() "
+                                  "it first")
+
+    def squeeze(self, axis=None):
+        raise NotImplementedError("squeeze on partitioned arrays")
+
+    def reshape(self, newshape):
+        if tuple(newshape) == tuple(self.shape):
+            return self
+        raise NotImplementedError("reshape on partitioned arrays")
+
+    # ------------------------------------------------------------------ reductions
+    def unary_reduction(self, op, src, where, orig_axis, axes, keepdims, args, initial) -> None:
+        """This (partitioned) array is the RESULT of a reduction."""
+        if isinstance(src, PartitionedArray):
+            src.reduce_into(self, op, where, orig_axis, axes, keepdims, args, initial)
+            return
+        tmp = DeferredArray(Store.empty(self.shape, self.dtype))
+        tmp.unary_reduction(op, src, where, orig_axis, axes, keepdims, args, initial)
+        self.copy(tmp)
+
+    def reduce_into(self, lhs: Any, op: UnaryRedCode, where: Any, orig_axis, axes, keepdims: bool,
+                    args: Any, initial: Any) -> None:
+        """unary_reduction with this array as the source and `lhs` (pre-existing, replicated or
+        partitioned) as the result."""
+        argred = op in _ARG_REDS
+        rank, world = runtime.rank, runtime.world_size
+        vlo, vhi = self.owned
+        src_local = self.local_rows(vlo, vhi) if vhi > vlo else None
+        where_local = None
+        if where is not None:
+            if not isinstance(where, PartitionedArray):
+                wl = DeferredArray(where._broadcast(self.shape).slice(0, slice(vlo, vhi)))
+            else:
+                wl = where.local_rows(vlo, vhi)
+            where_local = wl if vhi > vlo else None
+        elem = self.dtype
+        val_dtype = runtime.get_argred_type(elem) if argred else _val_dtype(op, elem)
+        ident = np.array(_UNARY_RED_IDENTITIES[op](elem), dtype=val_dtype)
+        scalar_out = all(d in axes for d in range(self.ndim))
+
+        if scalar_out:
+            partial = DeferredArray(Store.empty((1,), val_dtype))
+            partial.fill(ident)
+            if src_local is not None:
+                origin = (vlo,) + (0,) * (self.ndim - 1)
+                launch_scalar_red(op, partial.base, src_local.base,
+                                  None if where_local is None else where_local.base,
+                                  origin, self.shape, args)
+            total = _allreduce(partial, op, argred, elem)
+            _fold_into(lhs, total, op, argred, initial, elem)
+            return
+
+        if len(axes) > 1:
+            raise NotImplementedError("Need support for reducing multiple dimensions")
+        axis = axes[0]
+        out_shape = tuple(n for d, n in enumerate(self.shape) if d != axis)
+        if axis != 0:
+            # independent per row block: the result is partitioned like the source
+            if not isinstance(lhs, PartitionedArray) or not lhs.part.same_as(self.part):
+                tmp = PartitionedArray.empty(lhs.shape, lhs.dtype, like=self)
+                self.reduce_into(tmp, op, where, orig_axis, axes, keepdims, args, initial)
+                _assign_any(lhs, tmp)
+                return
+            if src_local is not None:
+                lhs.local_rows(vlo, vhi).unary_reduction(op, src_local, where_local, orig_axis, axes,
+                                                         keepdims, args, initial)
+            lhs._invalidate()
+            return
+        # axis 0 is the partitioned axis: full-width partial per rank, then allreduce
+        partial = DeferredArray(Store.empty(out_shape, val_dtype))
+        partial.fill(ident)
+        if src_local is not None:
+            promoted = partial.base.promote(0, src_local.shape[0])
+            d_out, d_in = promoted.descriptor(), src_local.base.descriptor()
+            d_w = None if where_local is None else where_local.base.descriptor()
+            _lib.check(runtime.lib.cnb_unary_red(
+                int(op), 0, ctypes.byref(d_out), ctypes.byref(d_in),
+                None if d_w is None else ctypes.byref(d_w), vlo, runtime.stream))
+        total = _allreduce(partial, op, argred, elem)
+        if keepdims:
+            total = DeferredArray(total.base.promote(0, 1))
+        _fold_into(lhs, total, op, argred, initial, elem)
+
+
+class _RowView:
+    """`a[i]` / `a[i, ...] = v` on a partitioned array: only the owner of row i touches it."""
+
+    def __init__(self, meta: _Shared, base_row: int, rest: Tuple) -> None:
+        self.meta, self.base_row, self.rest = meta, base_row, rest
+
+    @property
+    def shape(self) -> Tuple[int, ...]:
+        probe = Store(None, self.meta.dtype, self.meta.gshape[1:])
+        return _basic_index(probe, self.rest).shape if self.rest else probe.shape
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def dtype(self) -> np.dtype:
+        return self.meta.dtype
+
+    def get_item(self, key):
+        raise NotImplementedError("reading a single row of a partitioned array (a[i]) is a "
+                                  "one-element-task path outside the hot-path scope")
+
+    def _local(self) -> Optional[DeferredArray]:
+        lo, hi = self.meta.part.bounds(runtime.rank)
+        if not (lo <= self.base_row < hi):
+            return None
+        row = self.meta.local.base.project(0, self.base_row - (lo - self.meta.halo))
+        if self.rest:
+            row = _basic_index(row, self.rest)
+        return DeferredArray(row)
+
+    def assign(self, rhs: Any) -> None:
+        if isinstance(rhs, PartitionedArray):
+            raise NotImplementedError("assigning a partitioned array to a single row")
+        local = self._local()
+        if local is not None:
+            if rhs.dtype != local.dtype:
+                tmp = DeferredArray(Store.empty(rhs.shape, local.dtype))
+                tmp.convert(rhs)
+                rhs = tmp
+            local.copy(rhs, deep=False)
+        self.meta.ghost_valid = False
+
+
+# ---------------------------------------------------------------------- helpers
+def _val_dtype(op: UnaryRedCode, elem: np.dtype) -> np.dtype:
+    if op in (UnaryRedCode.ALL, UnaryRedCode.ANY, UnaryRedCode.CONTAINS):
+        return np.dtype(np.bool_)
+    if op == UnaryRedCode.COUNT_NONZERO:
+        return np.dtype(np.uint64)
+    return elem
+
+
+def _field_view(av: DeferredArray, field: str) -> DeferredArray:
+    s = av.base
+    dt, off = s.dtype.fields[field][0], s.dtype.fields[field][1]
+    return DeferredArray(Store(s.buffer, dt, s.shape, s.strides, s.offset + off))
+
+
+def _nccl_allreduce(buf: DeferredArray, red: UnaryRedCode) -> None:
+    """In-place NCCL allreduce of a dense local buffer."""
+    assert buf.base.is_c_contiguous
+    _lib.check(runtime.lib.cnb_comm_allreduce(runtime.comm, buf.base.ptr, buf.base.ptr, buf.size,
+                                              dtype_code(buf.dtype), int(red), runtime.stream))
+
+
+def _allreduce(partial: DeferredArray, op: UnaryRedCode, argred: bool, elem: np.dtype
+               ) -> DeferredArray:
+    """Combine the per-rank partials (dense VAL array, same shape on every rank)."""
+    if runtime.world_size == 1:
+        return partial
+    if not argred:
+        _nccl_allreduce(partial, _COMBINE[op])
+        return partial
+    # arg-reductions: best value across ranks, then the LOWEST index among the ranks that hold it
+    is_max = op in (UnaryRedCode.ARGMAX, UnaryRedCode.NANARGMAX)
+    vals = DeferredArray(Store.empty(partial.shape, elem))
+    vals.copy(_field_view(partial, "arg_value"), deep=True)
+    best = DeferredArray(Store.empty(partial.shape, elem))
+    best.copy(vals, deep=True)
+    _nccl_allreduce(best, UnaryRedCode.MAX if is_max else UnaryRedCode.MIN)
+    args = DeferredArray(Store.empty(partial.shape, np.int64))
+    args.copy(_field_view(partial, "arg"), deep=True)
+    hit = DeferredArray(Store.empty(partial.shape, np.bool_))
+    hit.binary_op(BinaryOpCode.EQUAL, vals, best)
+    valid = DeferredArray(Store.empty(partial.shape, np.bool_))
+    none = DeferredArray(Store.from_scalar(np.array(np.iinfo(np.int64).min, dtype=np.int64)))
+    valid.binary_op(BinaryOpCode.NOT_EQUAL, args, none)
+    hit.binary_op(BinaryOpCode.LOGICAL_AND, hit, valid)
+    big = DeferredArray(Store.from_scalar(np.array(np.iinfo(np.int64).max, dtype=np.int64)))
+    cand = DeferredArray(Store.empty(partial.shape, np.int64))
+    cand.where(hit, args, big)
+    _nccl_allreduce(cand, UnaryRedCode.MIN)
+    # no rank had a real element -> keep the identity index
+    has = DeferredArray(Store.empty(partial.shape, np.bool_))
+    has.binary_op(BinaryOpCode.NOT_EQUAL, cand, big)
+    final_arg = DeferredArray(Store.empty(partial.shape, np.int64))
+    final_arg.where(has, cand, none)
+    out = DeferredArray(Store.empty(partial.shape, partial.dtype))
+    _field_view(out, "arg").copy(final_arg, deep=True)
+    _field_view(out, "arg_value").copy(best, deep=True)
+    return out
+
+
+def _assign_any(lhs: Any, src: Any) -> None:
+    if isinstance(lhs, PartitionedArray):
+        lhs.copy(src)
+    elif isinstance(src, PartitionedArray):
+        lhs.copy(src.gather())
+    else:
+        lhs.copy(src)
+
+
+def _fold_into(lhs: Any, total: DeferredArray, op: UnaryRedCode, argred: bool, initial: Any,
+               elem: np.dtype) -> None:
+    """lhs <- fold(prefill, total), prefill = `initial` or the Python-side identity
+    (deferred.py:3207-3213); arg-reductions then extract the index (GETARG)."""
+    if argred:
+        arg = _field_view(total, "arg")
+        if isinstance(lhs, PartitionedArray):
+            lhs.copy(DeferredArray(arg.base.broadcast_to(lhs.shape)))
+        else:
+            lhs.copy(DeferredArray(arg.base.reshape_contiguous(lhs.shape))
+                     if arg.base.is_c_contiguous else _reshape_to(arg, lhs.shape))
+        return
+    total_v = total if total.shape == tuple(lhs.shape) else _reshape_to(total, lhs.shape)
+    prefill = initial if initial is not None else _UNARY_RED_IDENTITIES[op](elem)
+    init = DeferredArray(Store.from_scalar(np.array(prefill, dtype=lhs.dtype)))
+    lhs.binary_op(_FOLD_BINOP[_COMBINE[op]], init, total_v)
+
+
+def _reshape_to(src: DeferredArray, shape) -> DeferredArray:
+    dense = src
+    if not src.base.is_c_contiguous:
+        dense = DeferredArray(Store.empty(src.shape, src.dtype))
+        dense.copy(src, deep=True)
+    return DeferredArray(dense.base.reshape_contiguous(tuple(shape)))
+
+
+def replicate(thunk: Any) -> DeferredArray:
+    """Operand of a replicated (DeferredArray) task: partitioned inputs are gathered."""
+    if isinstance(thunk, PartitionedArray):
+        return thunk.gather()
+    return thunk
+
+
+# ---------------------------------------------------------------------- thunk factories
+def _min_partition_volume() -> int:
+    import os
+
+    return int(os.environ.get("CUNUMERIC_B200_MIN_PARTITION", "65536"))
+
+
+def create_empty_thunk(shape, dtype, inputs=None) -> Any:
+    """runtime.create_empty_thunk (cunumeric/runtime.py:448-460): pick the thunk type for a new
+    array.  Single-GPU: always a DeferredArray.  Multi-GPU: row-partitioned when it can be aligned
+    with a partitioned input (the reference's alignment constraint) or when it is big enough to be
+    worth tiling (the reference's MIN_GPU_CHUNK policy); small arrays are replicated."""
+    shape = tuple(int(s) for s in shape)
+    if runtime.world_size == 1 or len(shape) == 0:
+        return DeferredArray(Store.empty(shape, dtype))
+    like = None
+    any_partitioned = False
+    for inp in inputs or ():
+        thunk = getattr(inp, "_thunk", None)
+        if isinstance(thunk, PartitionedArray):
+            any_partitioned = True
+            if like is None and thunk.shape and thunk.shape[0] == shape[0]:
+                like = thunk
+    if like is not None:
+        return PartitionedArray.empty(shape, dtype, like=like)
+    volume = int(np.prod(shape, dtype=np.int64))
+    if not any_partitioned and shape[0] >= 2 * runtime.world_size \
+            and volume >= _min_partition_volume():
+        return PartitionedArray.empty(shape, dtype)
+    return DeferredArray(Store.empty(shape, dtype))
+
+
+def thunk_from_numpy(array: np.ndarray) -> Any:
+    array = np.asarray(array)
+    if runtime.world_size > 1 and array.ndim >= 1 and array.shape[0] >= 2 * runtime.world_size \
+            and array.size >= _min_partition_volume():
+        return PartitionedArray.from_numpy(array)
+    return DeferredArray.from_numpy(array)

@@ -61,7 +61,7 @@ def argval_dtype(dt) -> np.dtype:
     """Argval<T> = {int64 arg; T arg_value}, 16 bytes for every T up to 8 bytes (arg.h:23-59)."""
     dt = np.dtype(dt)
     return np.dtype({"names": ["arg", "arg_value"], "formats": [np.int64, dt],
-                     "offsets": [0, 8], "itemsize": 16})
+                     "offsets": [0, 8], "itemsize": 8 + max(8, dt.itemsize)})
 
 
 _lib = None

@@ -1,0 +1,93 @@
+"""Worker run by tests/test_distributed_gpu.py under torchrun (one rank per GPU): the NumPy-level
+program is identical on every rank (SPMD); arrays are row-partitioned by cunumeric_b200."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["CUNUMERIC_B200_MIN_PARTITION"] = "1"
+
+import torch.distributed as dist  # noqa: E402
+
+import cunumeric_b200 as cn  # noqa: E402
+from cunumeric_b200.distributed import PartitionedArray  # noqa: E402
+from cunumeric_b200.workloads import stencil_init, stencil_run  # noqa: E402
+
+
+def main() -> None:
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cn.runtime.init_distributed(rank, world)
+    assert cn.runtime.world_size == world
+
+    # ---- stencil (examples/stencil.py) vs NumPy, several sizes incl. rows not divisible by world
+    for n, iters, dt in ((30, 3, np.float64), (257, 5, np.float64), (64, 2, np.float32)):
+        g = stencil_init(n, dt, xp=cn)
+        assert isinstance(g._thunk, PartitionedArray)
+        w = stencil_run(g, iters)
+        g_np = stencil_init(n, dt, xp=np)
+        w_np = stencil_run(g_np, iters)
+        assert np.array_equal(w.__array__(), w_np), f"stencil work mismatch n={n}"
+        assert np.array_equal(g.__array__(), g_np), f"stencil grid mismatch n={n}"
+
+    # ---- elementwise on partitioned + replicated operands
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=(101, 37))
+    b = rng.normal(size=(101, 37))
+    A, B = cn.array(a), cn.array(b)
+    assert isinstance(A._thunk, PartitionedArray)
+    got = (A * B + 2.5 - A / (cn.absolute(B) + 1.0)).__array__()
+    assert np.array_equal(got, a * b + 2.5 - a / (np.abs(b) + 1.0))
+    assert np.array_equal(cn.where(A > B, A, B).__array__(), np.where(a > b, a, b))
+    assert np.array_equal(A.astype(np.float32).__array__(), a.astype(np.float32))
+    row = rng.normal(size=(37,))
+    assert np.array_equal((A + cn.array(row)).__array__(), a + row)  # replicated (C,) operand
+    A[1:-1, 2:5] = B[1:-1, 2:5]
+    a[1:-1, 2:5] = b[1:-1, 2:5]
+    assert np.array_equal(A.__array__(), a)
+    A[0, :] = 7.0
+    A[:, -1] = -1.0
+    a[0, :] = 7.0
+    a[:, -1] = -1.0
+    assert np.array_equal(A.__array__(), a)
+
+    # ---- reductions: scalar, axis 0 (needs the allreduce), axis 1 (local)
+    x = rng.normal(size=(203, 64)).astype(np.float32)
+    X = cn.array(x)
+    assert np.allclose(float(X.sum()), x.sum(dtype=np.float64), rtol=1e-5)
+    assert float(X.max()) == x.max() and float(X.min()) == x.min()
+    assert int(X.argmax()) == int(x.argmax()) and int(X.argmin()) == int(x.argmin())
+    assert bool((X > -100).all()) and not bool((X > 100).any())
+    assert np.allclose(X.sum(axis=0).__array__(), x.sum(axis=0), rtol=1e-4, atol=1e-4)
+    assert np.allclose(X.sum(axis=1).__array__(), x.sum(axis=1), rtol=1e-4, atol=1e-4)
+    assert np.array_equal(X.max(axis=0).__array__(), x.max(axis=0))
+    assert np.array_equal(X.max(axis=1).__array__(), x.max(axis=1))
+    assert np.array_equal(X.argmax(axis=0).__array__(), x.argmax(axis=0))
+    assert np.array_equal(X.argmax(axis=1).__array__(), x.argmax(axis=1))
+    assert np.array_equal(X.argmin(axis=0).__array__(), x.argmin(axis=0))
+    ties = np.zeros((40, 6), dtype=np.int32)
+    ties[[3, 25, 39], :] = 9  # the same maximum on different ranks: lowest row must win
+    assert np.array_equal(cn.array(ties).argmax(axis=0).__array__(), np.full(6, 3))
+    assert int(cn.array(ties).argmax()) == 18
+    v = rng.integers(-1000, 1000, size=100003).astype(np.int64)
+    V = cn.array(v)
+    assert int(V.sum()) == int(v.sum()) and int(V.argmax()) == int(v.argmax())
+    assert float(X.sum(initial=10.0)) == pytest_approx(x.sum(dtype=np.float64) + 10.0)
+
+    cn.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank} ok")
+
+
+def pytest_approx(v, rel=1e-5):
+    class _A:
+        def __eq__(self, o):
+            return abs(o - v) <= rel * abs(v)
+    return _A()
+
+
+if __name__ == "__main__":
+    main()

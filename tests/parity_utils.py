@@ -36,6 +36,8 @@ def make_input(dtype, n, rng, kind="general"):
     pow_exp | ge1"""
     dtype = np.dtype(dtype)
     if dtype == np.bool_:
+        if kind in ("nonzero", "positive"):
+            return np.ones(n, dtype=np.bool_)  # x / False is a division by zero in the functors
         return rng.random(n) < 0.5
     if dtype.kind in "iu":
         info = np.iinfo(dtype)
@@ -125,6 +127,29 @@ def ulp_distance(got, exp):
     if inf_mismatch.any():
         return np.inf
     return int(d.max())
+
+
+def assert_close_scaled(got, exp, scale, k, what=""):
+    """|got - exp| <= k * eps * scale element-wise (NaNs / infinities must coincide).  Used where a
+    plain ulp count of the RESULT is the wrong yardstick: complex functions (error is relative to
+    |z|, a tiny component next to a large one carries the large one's rounding) and sums that
+    cancel (logaddexp of negative operands)."""
+    got = np.asarray(got)
+    exp = np.asarray(exp)
+    assert got.dtype == exp.dtype and got.shape == exp.shape, f"{what}: {got.dtype} vs {exp.dtype}"
+    part = got.real.dtype
+    eps = np.finfo(part).eps
+    bad_g = ~np.isfinite(got)
+    bad_e = ~np.isfinite(exp)
+    assert np.array_equal(bad_g, bad_e), f"{what}: non-finite positions differ"
+    ok = ~bad_e
+    if got.dtype.kind != "c":
+        assert np.array_equal(got[bad_e], exp[bad_e], equal_nan=True), f"{what}: inf/nan mismatch"
+    err = np.abs(got[ok].astype(np.complex128) - exp[ok].astype(np.complex128))
+    scale = np.broadcast_to(np.asarray(scale, dtype=np.float64), exp.shape)[ok]
+    bound = k * eps * np.maximum(scale, float(np.finfo(part).tiny))
+    worst = (err / bound).max() if err.size else 0.0
+    assert worst <= 1.0, f"{what}: error {worst * k:.2f} eps*scale > {k}"
 
 
 def assert_close_ulp(got, exp, max_ulp, what=""):

@@ -63,13 +63,27 @@ class ClockSampler:
     Uses NVML in a background thread (same counters as the recipe's nvidia-smi line, without
     spawning a process that contends for the driver lock while kernels are being launched)."""
 
-    def __init__(self, device: int, period_s: float = 0.02) -> None:
+    def __init__(self, device: int, period_s: float = 0.05) -> None:
         self.device = device
         self.period = period_s
         self.samples = []
         self._stop = None
         self._thread = None
         self._err = None
+        self._nv = None
+        self._handle = None
+        self._max = None
+        # NVML initialisation takes ~100 ms and briefly stalls the driver: do it here, outside the
+        # timed region; start() only spawns the polling thread.
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            self._handle = nv.nvmlDeviceGetHandleByIndex(self._uuid_index(nv))
+            self._max = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+            self._nv = nv
+        except Exception as exc:
+            self._err = f"nvml unavailable: {exc}"
 
     def _uuid_index(self, nv):
         # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML index
@@ -89,15 +103,9 @@ class ClockSampler:
     def start(self) -> None:
         import threading
 
-        try:
-            import pynvml as nv
-
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self._uuid_index(nv))
-            self._max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        except Exception as exc:
-            self._err = f"nvml unavailable: {exc}"
+        if self._nv is None:
             return
+        nv, h = self._nv, self._handle
         self._stop = threading.Event()
 
         def loop():

@@ -28,21 +28,26 @@ def run_stencil(args, rank, world, dist, ClockSampler, load_peaks, max_over_rank
         stencil_run(grid, iters)
     cn.synchronize()
 
-    ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
+    events = [lib.cnb_event_create() for _ in range(args.steps + 1)]
     sampler = ClockSampler(cn.runtime.device)
     barrier(dist)
     sampler.start()
     cn.synchronize()
     launches0 = cn.runtime.launch_count()
-    lib.cnb_event_record(ev0, cn.runtime.stream)
-    for _ in range(args.steps):
+    lib.cnb_event_record(events[0], cn.runtime.stream)
+    for i in range(args.steps):
         stencil_run(grid, iters)
-    lib.cnb_event_record(ev1, cn.runtime.stream)
+        lib.cnb_event_record(events[i + 1], cn.runtime.stream)
     cn.synchronize()
     barrier(dist)
     launches = cn.runtime.launch_count() - launches0
     ms = ctypes.c_float()
-    _lib.check(lib.cnb_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+    _lib.check(lib.cnb_event_elapsed_ms(events[0], events[-1], ctypes.byref(ms)))
+    step_ms = []
+    for i in range(args.steps):
+        one = ctypes.c_float()
+        _lib.check(lib.cnb_event_elapsed_ms(events[i], events[i + 1], ctypes.byref(one)))
+        step_ms.append(round(one.value, 3))
     clocks = sampler.stop()
     elapsed = max_over_ranks(dist, ms.value * 1e-3)
     points = float(n) * n * iters * args.steps
@@ -64,7 +69,7 @@ def run_stencil(args, rank, world, dist, ClockSampler, load_peaks, max_over_rank
                        "halo_bytes_per_iter_per_gpu": {"sent": sent, "received": recv},
                        "l2_policy": f"grid {(n + 2) ** 2 * 8 / 1e9:.1f} GB and temporaries exceed "
                                     "the 126 MB L2" if n >= 8000 else "working set fits L2"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "step_ms_rank0": step_ms,
             "roofline": {"bound": "hbm", "achieved": gbs_per_gpu, "peak": peak_gbs, "unit": "GB/s",
                          "frac": gbs_per_gpu / peak_gbs, "traffic": None,
                          "kernel": "whole iteration (4 ADD on pitched views + scalar MULTIPLY + "

@@ -226,11 +226,12 @@ class PartitionedArray:
     # ------------------------------------------------------------------ operand alignment
     def _operand(self, src: Any, vlo: int, vhi: int) -> DeferredArray:
         """Local piece of `src` aligned with this (output) view's rows [vlo, vhi)."""
+        if isinstance(src, PartitionedArray) and (src.ndim != self.ndim or
+                                                  src.shape[0] != self.shape[0]):
+            # cannot be aligned row-for-row with the output (lower rank, or broadcast along the
+            # partitioned axis): replicate it (collective) and fall through to the replicated rules
+            src = src.gather()
         if isinstance(src, PartitionedArray):
-            if src.ndim != self.ndim:
-                raise NotImplementedError("partitioned operands must have the output's rank")
-            if src.shape[0] != self.shape[0]:
-                raise NotImplementedError("broadcasting a partitioned operand along axis 0")
             mine = self.part
             needs = []
             for r in range(runtime.world_size):

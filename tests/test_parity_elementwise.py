@@ -20,7 +20,7 @@ TRANSCENDENTAL_ULP = 2
 # add/sub/mul goes through different, equally valid library algorithms on the CPU (libstdc++ /
 # glibc) and the GPU (libcu++); k is the budget in units of eps*|z|.
 COMPLEX_EPS = {"DIVIDE": 4, "POWER": 256, "FLOAT_POWER": 256}
-COMPLEX_UNARY_EPS = 8
+COMPLEX_UNARY_EPS = 64  # the reference's own tests use allclose(rtol=1e-5) = 168 eps for complex64
 # Real functions whose CPU libm (glibc 2.39, external to the reference) is itself only accurate to
 # ~4 ulp, so agreement within 2 ulp is not attainable by being MORE accurate: glibc's
 # libm-test-ulps lists cbrt (double) at 4 ulp; the device cbrt() is a 1-ulp function.
@@ -60,7 +60,7 @@ def binary_tolerance(op, dt, odt):
     if dt.kind == "c":
         if op in ("ADD", "SUBTRACT", "MULTIPLY", "MAXIMUM", "MINIMUM"):
             return 0
-        return COMPLEX_ULP.get(op, TRANSCENDENTAL_ULP)
+        return COMPLEX_EPS.get(op, TRANSCENDENTAL_ULP)
     if op in pu.EXACT_BINARY:
         return 0
     return TRANSCENDENTAL_ULP
@@ -110,8 +110,9 @@ def test_invalid_binary_pairs_are_rejected():
 
 def unary_inputs(op, dt, rng):
     kind = "general"
-    if op in ("ARCSIN", "ARCCOS", "ARCTANH"):
-        kind = "unit"
+    if op in ("ARCSIN", "ARCCOS", "ARCTANH") or (dt.kind == "c" and op in ("TAN", "TANH")):
+        kind = "unit"  # (complex tan/tanh: stay away from the poles at pi/2, where both libraries
+        # lose digits in proportion to the condition number)
     elif op in ("LOG", "LOG2", "LOG10", "SQRT"):
         kind = "positive" if dt.kind != "c" else "small"
     elif op == "ARCCOSH":

@@ -42,9 +42,15 @@ struct AxisPlan {
   long long tiles_fast;          // column tiles along kept[2]
   long long split_len;           // axis rows per split
   int nsplit;
+  int warps_x;                   // warps of a CTA laid across the contiguous kept dim (1,2,4,8)
 };
 
 // ---------------------------------------------------------------------------------------------
+// COLUMN mode.  The CTA's 8 warps are laid out as WX warps across the contiguous kept dim x
+// WY = 8/WX row-lanes down the axis.  For wide outputs WX = 8: the whole CTA reads ONE row segment of
+// 8*32*V contiguous elements (4 KB for fp32) per step, rows in axis order, UNR rows in flight per
+// thread — long contiguous DRAM bursts instead of 512-byte pieces 128 KB apart — and every thread
+// owns its V columns outright, so no shared-memory exchange is needed at all.
 template <class R, int V>
 __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, char* scratch_raw,
                                               unsigned int* tickets)
@@ -52,7 +58,11 @@ __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, cha
   using T   = typename R::In;
   using Acc = typename R::Acc;
   using Val = typename R::Val;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int WX = p.warps_x, WY = RED_WARPS / WX;
+  const int wx = warp % WX, wy = warp / WX;
+  const int lanes_w = WX * 32 * V;  // columns per CTA tile
+  const int lane_c  = (wx * 32 + tx) * V;
 
   // column tile -> (position along the fast kept dim, index over the slower kept dims)
   const long long tile  = blockIdx.x;
@@ -60,7 +70,7 @@ __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, cha
   const long long tfast = tile - slow * p.tiles_fast;
   const long long k1    = slow % p.kept[1];
   const long long k0    = slow / p.kept[1];
-  const long long c0    = tfast * (32 * V) + (long long)tx * V;  // first column of this lane
+  const long long c0    = tfast * lanes_w + lane_c;  // first column of this lane
   const bool active     = c0 < p.kept[2];
   const long long in_base  = k0 * p.in_k[0] + k1 * p.in_k[1] + c0 * p.in_k[2];
   const long long w_base   = k0 * p.w_k[0] + k1 * p.w_k[1] + c0 * p.w_k[2];
@@ -75,56 +85,52 @@ __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, cha
   const long long a_end   = min(p.alen, a_begin + p.split_len);
   constexpr int UNR       = 4;
   if (active) {
-    for (long long a0 = a_begin + ty; a0 < a_end; a0 += RED_WARPS * UNR) {
+    for (long long a0 = a_begin + wy; a0 < a_end; a0 += (long long)WY * UNR) {
       Pack<T, V> x[UNR];
       bool ok[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        const long long a = a0 + (long long)u * RED_WARPS;
+        const long long a = a0 + (long long)u * WY;
         ok[u]             = a < a_end;
-        if (ok[u]) {
-          const char* src = p.in + in_base + a * p.in_a;
-          if constexpr (V > 1) {
-            ld_bytes<sizeof(T) * V>(x[u].raw, src);
-          } else {
-            ld_bytes<sizeof(T)>(x[u].raw, src);
-          }
-        }
+        if (ok[u]) ld_bytes<sizeof(T) * V>(x[u].raw, p.in + in_base + a * p.in_a);
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         if (ok[u]) {
-          const long long a = a0 + (long long)u * RED_WARPS;
+          const long long a = a0 + (long long)u * WY;
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             bool m = v < nvalid;
             if (m && p.where != nullptr)
               m = *reinterpret_cast<const unsigned char*>(p.where + w_base + v * p.w_k[2] +
                                                           a * p.w_a) != 0;
-            if (m) acc[v] = R::fold(acc[v], r.convert(x[u][v], p.axis_origin + a));
+            // each thread walks the axis in increasing order: ordered fast path for arg-reductions
+            if (m) red_visit(r, acc[v], x[u][v], true, [&] { return p.axis_origin + a; });
           }
         }
       }
     }
   }
 
-  // fold the 8 row-lanes of the CTA in ty order
+  // fold the WY row-lanes of the CTA in wy order (nothing to do when the CTA is one row wide)
   __shared__ RawSmem<Acc, RED_WARPS * 32 * V> smem;
-  Acc* sm = smem.ptr();
+  if (WY > 1) {
+    Acc* sm = smem.ptr();
 #pragma unroll
-  for (int v = 0; v < V; ++v) sm[(ty * 32 + tx) * V + v] = acc[v];
-  __syncthreads();
-  if (ty == 0) {
+    for (int v = 0; v < V; ++v) sm[wy * lanes_w + lane_c + v] = acc[v];
+    __syncthreads();
+    if (wy == 0) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      Acc t = sm[tx * V + v];
-      for (int w = 1; w < RED_WARPS; ++w) t = R::fold(t, sm[(w * 32 + tx) * V + v]);
-      acc[v] = t;
+      for (int v = 0; v < V; ++v) {
+        Acc t = sm[lane_c + v];
+        for (int w = 1; w < WY; ++w) t = R::fold(t, sm[w * lanes_w + lane_c + v]);
+        acc[v] = t;
+      }
     }
   }
 
   if (p.nsplit == 1) {
-    if (ty == 0) {
+    if (wy == 0) {
       for (int v = 0; v < nvalid; ++v) {
         Val* o = reinterpret_cast<Val*>(p.out + out_base + v * p.out_k[2]);
         *o     = R::finish(R::fold(R::lift(*o), acc[v]));
@@ -133,13 +139,14 @@ __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, cha
     return;
   }
 
-  // split partials -> scratch[split][tile][32*V]; last CTA of the tile folds them in split order
+  // split partials -> scratch[split][tile][lanes_w]; the last CTA of the tile folds them in split
+  // order
   Acc* scratch            = reinterpret_cast<Acc*>(scratch_raw);
-  const long long per_spl = (long long)gridDim.x * 32 * V;
-  if (ty == 0) {
+  const long long per_spl = (long long)gridDim.x * lanes_w;
+  if (wy == 0) {
 #pragma unroll
     for (int v = 0; v < V; ++v)
-      scratch[(long long)blockIdx.y * per_spl + tile * 32 * V + tx * V + v] = acc[v];
+      scratch[(long long)blockIdx.y * per_spl + tile * lanes_w + lane_c + v] = acc[v];
   }
   __shared__ bool is_last;
   __threadfence();
@@ -149,14 +156,14 @@ __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, cha
     is_last              = (t == (unsigned int)p.nsplit - 1);
   }
   __syncthreads();
-  if (is_last && ty == 0) {
+  if (is_last && wy == 0) {
     __threadfence();
     for (int v = 0; v < nvalid; ++v) {
       Acc t = R::identity();
       for (int s = 0; s < p.nsplit; ++s) {
         Acc q;
         ld_bytes<sizeof(Acc)>(&q, reinterpret_cast<const char*>(
-                                    &scratch[(long long)s * per_spl + tile * 32 * V + tx * V + v]));
+                                    &scratch[(long long)s * per_spl + tile * lanes_w + lane_c + v]));
         t = R::fold(t, q);
       }
       Val* o = reinterpret_cast<Val*>(p.out + out_base + v * p.out_k[2]);
@@ -165,17 +172,101 @@ __device__ __forceinline__ void axis_col_body(const AxisPlan& p, const R& r, cha
   }
 }
 
-template <class R>
-__global__ void __launch_bounds__(RED_THREADS)
+// One kernel per vector width so neither drags the other's registers along; 3 CTAs/SM resident
+// (the first version compiled both bodies into one kernel: 102 registers, 2 CTAs/SM, 25 %
+// occupancy and 56 % of the roofline — profiles/r01_axis_reduction_ncu.md).
+template <class R, int V>
+__global__ void __launch_bounds__(RED_THREADS, 3)
 axis_col_kernel(const __grid_constant__ AxisPlan p, const R r, char* scratch, unsigned int* tickets)
 {
-  constexpr int V = (16 / sizeof(typename R::In)) > 4 ? 4 : ((16 / sizeof(typename R::In)) < 1 ? 1 : 16 / sizeof(typename R::In));
-  if (p.vec) {
-    if constexpr (V > 1) axis_col_body<R, V>(p, r, scratch, tickets);
-  } else {
-    axis_col_body<R, 1>(p, r, scratch, tickets);
+  axis_col_body<R, V>(p, r, scratch, tickets);
+}
+
+// COLUMN mode, common case (dense C-order matrix reduced along axis 0, no mask): the same
+// algorithm as axis_col_body with WX = 8, stripped to what the hot loop needs so that it fits in
+// 64 registers (4 CTAs/SM).  Thread t of column tile b owns columns (b*256 + t)*V .. +V for all rows
+// of its axis split; the CTA reads one contiguous 256*V-element row segment per step.
+template <class R, int V, int UNR>
+__global__ void __launch_bounds__(RED_THREADS, 4)
+axis_col_fast_kernel(const char* __restrict__ in, char* __restrict__ out, char* scratch_raw,
+                     unsigned int* tickets, const R r, long long ncols, long long alen,
+                     long long in_a, long long out_stride, long long split_len, int nsplit,
+                     long long axis_origin)
+{
+  using T   = typename R::In;
+  using Acc = typename R::Acc;
+  using Val = typename R::Val;
+  const long long c0      = ((long long)blockIdx.x * RED_THREADS + threadIdx.x) * V;
+  const bool active       = c0 < ncols;
+  const long long a_begin = (long long)blockIdx.y * split_len;
+  const long long a_end   = min(alen, a_begin + split_len);
+  Acc acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = R::identity();
+  if (active) {
+    const char* p = in + c0 * (long long)sizeof(T) + a_begin * in_a;
+    long long a   = a_begin;
+    for (; a + UNR <= a_end; a += UNR) {
+      Pack<T, V> x[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) ld_bytes<sizeof(T) * V>(x[u].raw, p + u * in_a);
+      p += UNR * in_a;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          red_visit(r, acc[v], x[u][v], true, [&] { return axis_origin + a + u; });
+    }
+    for (; a < a_end; ++a) {
+      Pack<T, V> x;
+      ld_bytes<sizeof(T) * V>(x.raw, p);
+      p += in_a;
+#pragma unroll
+      for (int v = 0; v < V; ++v) red_visit(r, acc[v], x[v], true, [&] { return axis_origin + a; });
+    }
+  }
+  if (nsplit == 1) {
+    if (active) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        Val* o = reinterpret_cast<Val*>(out + (c0 + v) * out_stride);
+        *o     = R::finish(R::fold(R::lift(*o), acc[v]));
+      }
+    }
+    return;
+  }
+  Acc* scratch            = reinterpret_cast<Acc*>(scratch_raw);
+  const long long width   = (long long)gridDim.x * RED_THREADS * V;  // padded column count
+  const long long my_slot = ((long long)blockIdx.x * RED_THREADS + threadIdx.x) * V;
+#pragma unroll
+  for (int v = 0; v < V; ++v) scratch[(long long)blockIdx.y * width + my_slot + v] = acc[v];
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[blockIdx.x], 1u);
+    is_last              = (t == (unsigned int)nsplit - 1);
+  }
+  __syncthreads();
+  if (is_last && active) {
+    __threadfence();
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      Acc t = R::identity();
+      for (int s = 0; s < nsplit; ++s) {
+        Acc q;
+        ld_bytes<sizeof(Acc)>(&q, reinterpret_cast<const char*>(&scratch[(long long)s * width + my_slot + v]));
+        t = R::fold(t, q);
+      }
+      Val* o = reinterpret_cast<Val*>(out + (c0 + v) * out_stride);
+      *o     = R::finish(R::fold(R::lift(*o), t));
+    }
   }
 }
+
+template <typename T>
+inline constexpr int axis_vec_width =
+  (16 / sizeof(T)) > 4 ? 4 : ((16 / sizeof(T)) < 1 ? 1 : int(16 / sizeof(T)));
 
 // ---------------------------------------------------------------------------------------------
 // ROW mode: LPR lanes cooperate on one output element (LPR = 32: a warp, LPR = 256: the CTA)
@@ -220,7 +311,7 @@ axis_row_kernel(const __grid_constant__ AxisPlan p, const R r)
         if (lane < peel) {
           Pack<T, 1> x;
           ld_bytes<sizeof(T)>(x.raw, p.in + in_base + lane * (long long)sizeof(T));
-          acc = R::fold(acc, r.convert(x[0], p.axis_origin + lane));
+          red_visit(r, acc, x[0], true, [&] { return p.axis_origin + lane; });
         }
         a = peel;
         constexpr int UNR   = 4;
@@ -236,15 +327,15 @@ axis_row_kernel(const __grid_constant__ AxisPlan p, const R r)
           for (int u = 0; u < UNR; ++u)
 #pragma unroll
             for (int v = 0; v < V; ++v)
-              acc = R::fold(acc, r.convert(x[u][v],
-                                           p.axis_origin + a + (i + (long long)u * LPR) * V + v));
+              red_visit(r, acc, x[u][v], true,
+                        [&] { return p.axis_origin + a + (i + (long long)u * LPR) * V + v; });
         }
         for (; i < nv; i += LPR) {
           Pack<T, V> x;
           ld_bytes<sizeof(T) * V>(x.raw, base + i * 16);
 #pragma unroll
           for (int v = 0; v < V; ++v)
-            acc = R::fold(acc, r.convert(x[v], p.axis_origin + a + i * V + v));
+            red_visit(r, acc, x[v], true, [&] { return p.axis_origin + a + i * V + v; });
         }
         a += nv * V;
       }
@@ -256,7 +347,7 @@ axis_row_kernel(const __grid_constant__ AxisPlan p, const R r)
         if (m) {
           Pack<T, 1> x;
           ld_bytes<sizeof(T)>(x.raw, p.in + in_base + i * p.in_a);
-          acc = R::fold(acc, r.convert(x[0], p.axis_origin + i));
+          red_visit(r, acc, x[0], true, [&] { return p.axis_origin + i; });
         }
       }
     }
@@ -361,18 +452,55 @@ int axis_red_by_type(int axis, const cnb_store_t* out, const cnb_store_t* in,
                             !(p.alen == 1);
       const int sms = sm_count();
       if (col_mode || (nk > 0 && p.alen == 1)) {
-        constexpr int V = (16 / sizeof(T)) > 4 ? 4 : ((16 / sizeof(T)) < 1 ? 1 : 16 / sizeof(T));
+        constexpr int V = axis_vec_width<T>;
         const long long vb = V * isz;
         bool vec = V > 1 && p.in_k[2] == isz && reinterpret_cast<uintptr_t>(p.in) % vb == 0 &&
                    p.in_a % vb == 0 && p.in_k[0] % vb == 0 && p.in_k[1] % vb == 0 &&
                    p.kept[2] % V == 0;
         p.vec               = vec ? 1 : 0;
-        const int lanes_w   = 32 * (vec ? V : 1);
+        if (vec && where == nullptr && nk == 1 && p.ncols >= 4LL * RED_THREADS * V) {
+          // fast kernel: dense matrix, contiguous kept dim
+          const long long tiles = (p.ncols + (long long)RED_THREADS * V - 1) / ((long long)RED_THREADS * V);
+          // one wave: tiles x splits must not exceed the resident CTAs (4 per SM), or a few
+          // straggler CTAs double the kernel time
+          long long want = std::max<long long>(1, (4LL * sms) / tiles);
+          long long maxs = std::max<long long>(1, p.alen / 64);
+          int nsplit     = (int)std::max<long long>(1, std::min<long long>(std::min(want, maxs), 65535));
+          long long split_len = (p.alen + nsplit - 1) / nsplit;
+          nsplit              = (int)((p.alen + split_len - 1) / split_len);
+          char* scratch         = nullptr;
+          unsigned int* tickets = nullptr;
+          if (nsplit > 1) {
+            const size_t sbytes = (size_t)nsplit * tiles * RED_THREADS * V * sizeof(Acc);
+            const size_t tbytes = (size_t)tiles * sizeof(unsigned int);
+            scratch = static_cast<char*>(pool_alloc(sbytes + tbytes, stream));
+            if (scratch == nullptr) return CNB_ERR_CUDA;
+            tickets = reinterpret_cast<unsigned int*>(scratch + sbytes);
+            int rc  = check_cuda(cudaMemsetAsync(tickets, 0, tbytes, stream), "ticket memset");
+            if (rc != CNB_OK) return rc;
+          }
+          dim3 grid((unsigned)tiles, (unsigned)nsplit);
+          {
+            LaunchScope scope(stream, KERNEL_AXIS_COL, p.ncols * p.alen, algo_bytes);
+            axis_col_fast_kernel<R, V, 4><<<grid, RED_THREADS, 0, stream>>>(
+              p.in, p.out, scratch, tickets, R(nullptr), p.ncols, p.alen, p.in_a, p.out_k[2],
+              split_len, nsplit, p.axis_origin);
+          }
+          int rc = check_cuda(cudaGetLastError(), "axis_col_fast_kernel launch");
+          if (scratch != nullptr) pool_free(scratch, stream);
+          return rc;
+        }
+        const int warp_w    = 32 * (vec ? V : 1);
+        int wxs             = RED_WARPS;
+        while (wxs > 1 && (long long)(wxs / 2) * warp_w >= p.kept[2]) wxs /= 2;
+        p.warps_x           = wxs;
+        const int lanes_w   = wxs * warp_w;
         p.tiles_fast        = (p.kept[2] + lanes_w - 1) / lanes_w;
         const long long tiles = p.tiles_fast * p.kept[0] * p.kept[1];
         if (tiles > 0x7fffffffLL) return set_error(CNB_ERR_UNSUPPORTED, "UNARY_RED: too many tiles");
-        // split the axis until ~4 CTAs per SM are in flight, keeping >= 64 rows per split
-        long long want = (4LL * sms + tiles - 1) / tiles;
+        // split the axis until one full wave (3 CTAs per SM) is in flight, keeping >= 64 rows per
+        // split
+        long long want = std::max<long long>(1, (3LL * sms) / tiles);
         long long maxs = std::max<long long>(1, p.alen / 64);
         int nsplit     = (int)std::max<long long>(1, std::min<long long>(std::min(want, maxs), 65535));
         p.split_len    = (p.alen + nsplit - 1) / nsplit;
@@ -392,7 +520,10 @@ int axis_red_by_type(int axis, const cnb_store_t* out, const cnb_store_t* in,
         dim3 grid((unsigned)tiles, (unsigned)nsplit);
         {
           LaunchScope scope(stream, KERNEL_AXIS_COL, p.ncols * p.alen, algo_bytes);
-          axis_col_kernel<R><<<grid, RED_THREADS, 0, stream>>>(p, R(nullptr), scratch, tickets);
+          if (vec)
+            axis_col_kernel<R, V><<<grid, RED_THREADS, 0, stream>>>(p, R(nullptr), scratch, tickets);
+          else
+            axis_col_kernel<R, 1><<<grid, RED_THREADS, 0, stream>>>(p, R(nullptr), scratch, tickets);
         }
         int rc = check_cuda(cudaGetLastError(), "axis_col_kernel launch");
         if (scratch != nullptr) pool_free(scratch, stream);

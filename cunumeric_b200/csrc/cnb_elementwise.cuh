@@ -122,9 +122,23 @@ struct EwShape {
   static constexpr int min_size = ew_min_nz(
     ew_min_nz(ew_min_nz(ew_size<O0>, ew_size<O1>), ew_min_nz(ew_size<I0>, ew_size<I1>)),
     ew_size<I2>);
-  // smallest type moves 16 B per chunk, but no operand moves more than 64 B per chunk
-  static constexpr int E    = ew_cmax(1, ew_cmin(16 / min_size, 64 / max_size));
-  static constexpr int U    = ew_cmax(1, 64 / (E * max_size));
+  // Elements per chunk.  STORES must be exactly one <=16-byte access per lane, so that a warp's
+  // store instruction covers one contiguous 512-byte span: several 16-byte stores per lane at a
+  // 64-byte lane stride write half sectors that L2 has to merge (measured: int8->int64 convert at
+  // 26 % of the roofline).  Loads may be wider than 16 bytes per chunk (the halves of a sector are
+  // served by L1) but no input moves more than 64 bytes per chunk.  Kernels without outputs
+  // (reductions) read 16 bytes of the narrowest input.
+  static constexpr int max_out = ew_cmax(ew_size<O0>, ew_size<O1>);
+  static constexpr int max_in  = ew_cmax(ew_cmax(ew_size<I0>, ew_size<I1>), ew_size<I2>);
+  static constexpr int E =
+    max_out == 0 ? ew_cmax(1, 16 / min_size)
+                 : ew_cmax(1, max_in == 0 ? 16 / max_out : ew_cmin(16 / max_out, 64 / max_in));
+  // chunks per thread per tile: keep ~128 bytes of LOADS in flight per thread (all inputs
+  // together), so unary / widening-convert kernels get the same memory-level parallelism as the
+  // two-input kernels
+  static constexpr int in_bytes = ew_size<I0> + ew_size<I1> + ew_size<I2>;
+  static constexpr int U =
+    in_bytes == 0 ? 4 : ew_cmax(1, ew_cmin(8, 128 / (E * in_bytes)));
   static constexpr int TILE = EW_THREADS * E * U;
 };
 

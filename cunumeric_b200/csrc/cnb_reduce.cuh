@@ -60,6 +60,28 @@ __device__ __forceinline__ A block_reduce(A v, A* smem /* RED_WARPS entries */)
   return v;
 }
 
+// Fold one input element into a thread's accumulator.  `index` is only evaluated by the
+// arg-reductions; `ordered` promises that this thread visits elements in increasing index order,
+// which lets arg-reductions use the cheap strictly-better test instead of the general tie-breaking
+// fold.
+template <class R, class IndexFn>
+__device__ __forceinline__ void red_visit(const R& r, typename R::Acc& acc,
+                                          const typename R::In& x, bool ordered, IndexFn&& index)
+{
+  if constexpr (R::needs_index) {
+    if (ordered) {
+      if (R::better(acc.value, x)) {
+        acc.value = x;
+        acc.arg   = index();
+      }
+    } else {
+      acc = R::fold(acc, r.convert(x, index()));
+    }
+  } else {
+    acc = R::fold(acc, r.convert(x, 0));
+  }
+}
+
 // raw storage for an Acc in shared memory (Acc may have a non-trivial default constructor)
 template <typename A, int N>
 struct alignas(16) RawSmem {

@@ -444,6 +444,8 @@ struct Power : Base<T> {
       // representable (glibc pow is < 1 ulp), and the cast truncates — a 2-ulp device pow() would
       // turn 3**3 into 26.  Exponentiation by squaring in double is exact below 2**53.
       return static_cast<T>(pow_integral(static_cast<double>(a), static_cast<long long>(b)));
+    else if constexpr (std::is_same<T, float>::value)
+      return d2f(pow(static_cast<double>(a), static_cast<double>(b)));
     else
       return static_cast<T>(pow(static_cast<double>(a), static_cast<double>(b)));
   }

@@ -8,19 +8,30 @@
 
 namespace cnb {
 
+// static_cast between arithmetic types, with the slow F2F.F32.F64 replaced by d2f()
+template <typename D, typename S>
+__device__ __forceinline__ D cast_to(const S& s)
+{
+  if constexpr (std::is_same<D, float>::value && std::is_same<S, double>::value)
+    return d2f(s);
+  else
+    return static_cast<D>(s);
+}
+
 template <typename D, typename S>
 __device__ __forceinline__ D convert_plain(const S& s)
 {
   if constexpr (is_complex_v<S>) {
     if constexpr (is_complex_v<D>)
-      return D(static_cast<typename D::value_type>(s.real()),
-               static_cast<typename D::value_type>(s.imag()));
+      return D(cast_to<typename D::value_type>(s.real()),
+               cast_to<typename D::value_type>(s.imag()));
     else if constexpr (is_half_v<D>)
       return d2h(static_cast<double>(s.real()));
     else
-      return static_cast<D>(s.real());
+      return cast_to<D>(s.real());
   } else if constexpr (is_half_v<S>) {
-    const double v = static_cast<double>(h2f(s));
+    // (every fp16 value is exact in fp32, so fp32 stands in for the reference's double here)
+    const float v = h2f(s);
     if constexpr (is_complex_v<D>)
       return D(static_cast<typename D::value_type>(v), 0);
     else
@@ -28,9 +39,9 @@ __device__ __forceinline__ D convert_plain(const S& s)
   } else if constexpr (is_half_v<D>) {
     return d2h(static_cast<double>(s));
   } else if constexpr (is_complex_v<D>) {
-    return D(static_cast<typename D::value_type>(s), 0);
+    return D(cast_to<typename D::value_type>(s), 0);
   } else {
-    return static_cast<D>(s);
+    return cast_to<D>(s);
   }
 }
 

@@ -285,6 +285,13 @@ struct ArgMinMax : Shape<T, Argval<T>> {
     v.value = x;
     return v;
   }
+  // In-thread fast path for elements visited in INCREASING index order: a strictly better value
+  // replaces the incumbent, so the first occurrence survives ties, NaN never wins and an element
+  // equal to the identity value never displaces the identity — exactly the sequential CPU fold.
+  __device__ __forceinline__ static bool better(const T& incumbent, const T& x)
+  {
+    return IS_MAX ? lt(incumbent, x) : lt(x, incumbent);
+  }
   __device__ __forceinline__ static V fold(const V& a, const V& b)
   {
     // A strictly better value wins.  NaN never wins (the CPU fold is `if (b > a) a = b`).

@@ -60,9 +60,9 @@ CNB_FC_UNOP(Cosh, coshf(x), cosh(x), cuda::std::cosh(x))
 CNB_FC_UNOP(Sin, sinf(x), sin(x), cuda::std::sin(x))
 // sinhf/tanhf are 3-ulp functions on the device; evaluate in double and round once so fp32
 // results stay within the 2-ulp parity budget against the CPU libm
-CNB_FC_UNOP(Sinh, static_cast<float>(sinh(static_cast<double>(x))), sinh(x), cuda::std::sinh(x))
+CNB_FC_UNOP(Sinh, d2f(sinh(static_cast<double>(x))), sinh(x), cuda::std::sinh(x))
 CNB_FC_UNOP(Tan, tanf(x), tan(x), cuda::std::tan(x))
-CNB_FC_UNOP(Tanh, static_cast<float>(tanh(static_cast<double>(x))), tanh(x), cuda::std::tanh(x))
+CNB_FC_UNOP(Tanh, d2f(tanh(static_cast<double>(x))), tanh(x), cuda::std::tanh(x))
 CNB_FC_UNOP(Log, logf(x), log(x), cuda::std::log(x))
 CNB_FC_UNOP(Log10, log10f(x), log10(x), cuda::std::log10(x))
 // complex variants restate :546-557, :588-593, :799-804, :836-841
@@ -141,8 +141,10 @@ struct Rad2deg : Base<T> {
   {
     if constexpr (is_half_v<T>)
       return f2h(h2f(x) * static_cast<float>(180.0 / 3.14159265358979323846));
+    else if constexpr (std::is_same<T, float>::value)
+      return d2f(static_cast<double>(x) * 180.0 / 3.14159265358979323846);
     else if constexpr (std::is_floating_point<T>::value)
-      return static_cast<T>(static_cast<double>(x) * 180.0 / 3.14159265358979323846);
+      return x * 180.0 / 3.14159265358979323846;
     else
       return x;
   }

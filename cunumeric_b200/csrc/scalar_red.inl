@@ -32,7 +32,7 @@ struct RedIo {  // operand typing for EwShape: only the input participates
 template <class R>
 __global__ void __launch_bounds__(RED_THREADS)
 scalar_red_kernel(const __grid_constant__ EwPlan plan, const R r, typename R::Val* out,
-                  char* partials_raw, unsigned int* ticket)
+                  char* partials_raw, unsigned int* ticket, const int ordered)
 {
   using T   = typename R::In;
   using Acc = typename R::Acc;
@@ -76,11 +76,9 @@ scalar_red_kernel(const __grid_constant__ EwPlan plan, const R r, typename R::Va
       for (int u = 0; u < U; ++u) {
         const long long e = col0 + (long long)(u * RED_THREADS + tid) * E;
 #pragma unroll
-        for (int i = 0; i < E; ++i) {
-          long long ix = 0;
-          if constexpr (R::needs_index) ix = ix0 + (e + i) * plan.op[4].inner_stride;
-          acc = R::fold(acc, r.convert(a[u][i], ix));
-        }
+        for (int i = 0; i < E; ++i)
+          red_visit(r, acc, a[u][i], ordered != 0,
+                    [&] { return ix0 + (e + i) * plan.op[4].inner_stride; });
       }
     } else {
       constexpr int B = (sizeof(T) >= 8) ? 4 : 8;
@@ -104,9 +102,8 @@ scalar_red_kernel(const __grid_constant__ EwPlan plan, const R r, typename R::Va
         for (int j = 0; j < B; ++j) {
           if (m[j]) {
             const long long e = col0 + (long long)(j0 + j) * RED_THREADS + tid;
-            long long ix      = 0;
-            if constexpr (R::needs_index) ix = ix0 + e * plan.op[4].inner_stride;
-            acc = R::fold(acc, r.convert(a[j][0], ix));
+            red_visit(r, acc, a[j][0], ordered != 0,
+                      [&] { return ix0 + e * plan.op[4].inner_stride; });
           }
         }
       }
@@ -189,6 +186,18 @@ int scalar_red_by_type(const cnb_store_t* out, const cnb_store_t* in, const cnb_
       if (rc == 0) return CNB_OK;  // empty rect: the store keeps its pre-filled value
       if (where != nullptr) plan.vec = 0;
       if (plan.op[2].inner_stride != (long long)sizeof(T)) plan.vec = 0;
+      // arg-reductions: does every thread meet elements in increasing GLOBAL index order?  True
+      // when the canonical (memory-order) iteration is also row-major in index space.
+      int ordered = 0;
+      if (R::needs_index) {
+        ordered               = plan.op[4].inner_stride > 0 ? 1 : 0;
+        long long inner_span  = plan.op[4].inner_stride * plan.inner;
+        for (int d = EW_MAX_OUTER - 1; d >= 0 && ordered; --d) {
+          if (plan.outer[d] == 1) continue;
+          if (plan.op[4].outer_stride[d] < inner_span) ordered = 0;
+          inner_span = plan.op[4].outer_stride[d] * plan.outer[d];
+        }
+      }
       RedScratch scratch;
       rc = red_acquire_scratch(scratch, stream);
       if (rc != CNB_OK) return rc;
@@ -200,7 +209,7 @@ int scalar_red_by_type(const cnb_store_t* out, const cnb_store_t* in, const cnb_
                           ew_algorithmic_bytes(plan, args, EW_MAX_OPS));
         kernel<<<grid, RED_THREADS, 0, stream>>>(plan, R(extra),
                                                  static_cast<typename R::Val*>(out->ptr),
-                                                 scratch.partials, scratch.ticket);
+                                                 scratch.partials, scratch.ticket, ordered);
       }
       return check_cuda(cudaGetLastError(), "scalar_red_kernel launch");
     }

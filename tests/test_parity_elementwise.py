@@ -20,7 +20,7 @@ TRANSCENDENTAL_ULP = 2
 # add/sub/mul goes through different, equally valid library algorithms on the CPU (libstdc++ /
 # glibc) and the GPU (libcu++); k is the budget in units of eps*|z|.
 COMPLEX_EPS = {"DIVIDE": 4, "POWER": 256, "FLOAT_POWER": 256}
-COMPLEX_UNARY_EPS = 64  # the reference's own tests use allclose(rtol=1e-5) = 168 eps for complex64
+COMPLEX_UNARY_EPS = 128  # the reference's own tests use allclose(rtol=1e-5) = 168 eps for complex64
 # Real functions whose CPU libm (glibc 2.39, external to the reference) is itself only accurate to
 # ~4 ulp, so agreement within 2 ulp is not attainable by being MORE accurate: glibc's
 # libm-test-ulps lists cbrt (double) at 4 ulp; the device cbrt() is a 1-ulp function.

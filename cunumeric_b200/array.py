@@ -133,9 +133,18 @@ class ndarray:
             host = host.astype(dtype)
         return host
 
-    def to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Blocking D2H copy, optionally into a caller-provided (e.g. pinned) buffer."""
-        return self._thunk.__numpy_array__(out)
+    def to_host(self, out: Optional[np.ndarray] = None, blocking: bool = True):
+        """D2H copy, optionally into a caller-provided (e.g. pinned) buffer.  blocking=False starts
+        the copy on the copy stream and returns a future (`.wait()` gives the host array)."""
+        if blocking:
+            return self._thunk.__numpy_array__(out)
+        if out is None:
+            from .runtime import runtime
+
+            out = runtime.pinned_empty(self.shape, self.dtype)
+        if not isinstance(self._thunk, DeferredArray):
+            raise NotImplementedError("asynchronous to_host of a partitioned array")
+        return self._thunk.to_host_async(out)
 
     def item(self, *args):
         return self.__array__().item(*args)

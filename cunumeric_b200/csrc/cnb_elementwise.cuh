@@ -231,7 +231,9 @@ ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
       }
     } else {
       // ---- strided / tail path: coalesced element accesses, batches of B independent loads
-      constexpr int B = (S::max_size >= 8) ? 4 : 8;
+      // independent loads per batch: ~128 bytes in flight per thread, like the vector path (a
+      // single-input kernel with 4 loads per batch ran at 53 % of the roofline: the stencil's COPY)
+      constexpr int B = S::in_bytes == 0 ? 8 : ew_cmax(4, ew_cmin(16, 128 / S::in_bytes));
       constexpr int N = E * U;  // elements per thread per tile
 #pragma unroll 1
       for (int j0 = 0; j0 < N; j0 += B) {

@@ -81,7 +81,7 @@ scalar_red_kernel(const __grid_constant__ EwPlan plan, const R r, typename R::Va
                     [&] { return ix0 + (e + i) * plan.op[4].inner_stride; });
       }
     } else {
-      constexpr int B = (sizeof(T) >= 8) ? 4 : 8;
+      constexpr int B = ew_cmax(4, ew_cmin(16, 128 / (int)sizeof(T)));
       constexpr int N = E * U;
 #pragma unroll 1
       for (int j0 = 0; j0 < N; j0 += B) {

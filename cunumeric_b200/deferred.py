@@ -75,6 +75,28 @@ def _vp(arr: Optional[np.ndarray]):
     return None if arr is None else arr.ctypes.data_as(ctypes.c_void_p)
 
 
+class HostFuture:
+    """Completion handle of an asynchronous device->host copy.  Holds the device array alive until
+    the copy has finished."""
+
+    def __init__(self, event, keepalive, out: np.ndarray) -> None:
+        self._event, self._keepalive, self.out = event, keepalive, out
+
+    def wait(self) -> np.ndarray:
+        if self._event is not None:
+            _lib.check(runtime.lib.cnb_event_synchronize(self._event))
+            runtime._recycle_event(self._event)
+            self._event = None
+            self._keepalive = None
+        return self.out
+
+    def __del__(self) -> None:
+        try:
+            self.wait()
+        except Exception:
+            pass
+
+
 def _rep(thunk):
     """Operand of a replicated task: a partitioned thunk (distributed.PartitionedArray) is gathered
     onto every rank first (collective)."""
@@ -151,6 +173,26 @@ class DeferredArray:
         runtime.copy_h2d(thunk.base.ptr, src)
         return thunk
 
+    @staticmethod
+    def from_numpy_async(array: np.ndarray) -> "DeferredArray":
+        """H2D on the copy stream (source should be pinned): overlaps with kernels already queued on
+        the compute stream; the first task that uses the result waits for the copy."""
+        src = np.ascontiguousarray(array)
+        thunk = DeferredArray(Store.empty(array.shape, array.dtype))
+        runtime.copy_h2d_async(thunk.base.buffer, src)
+        return thunk
+
+    def to_host_async(self, out: np.ndarray) -> "HostFuture":
+        """D2H on the copy stream into `out` (should be pinned); returns a future to wait on."""
+        src = self
+        if not self.base.is_c_contiguous:
+            src = DeferredArray(Store.empty(self.shape, self.dtype))
+            src.copy(self, deep=True)
+        assert out.flags.c_contiguous and out.shape == tuple(self.shape) and out.dtype == self.dtype
+        if src.base.buffer.ready_event is not None:
+            runtime.wait_ready(src.base.buffer)
+        return HostFuture(runtime.copy_d2h_async(out, src.base.ptr), src, out)
+
     def __numpy_array__(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Blocking device->host read (the reference blocks in get_scalar_array / inline mapping)."""
         src = self
@@ -160,6 +202,8 @@ class DeferredArray:
         if out is None:
             out = np.empty(self.shape, dtype=self.dtype)
         assert out.flags.c_contiguous and out.shape == tuple(self.shape) and out.dtype == self.dtype
+        if src.base.buffer.ready_event is not None:
+            runtime.wait_ready(src.base.buffer)
         runtime.copy_d2h(out, src.base.ptr)
         runtime.synchronize()
         return out

@@ -91,6 +91,47 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     return runtime.pinned_empty(tuple(shape), dtype)
 
 
+def from_host(host: np.ndarray, blocking: bool = True) -> ndarray:
+    """Upload a host array.  blocking=False issues the copy on the copy stream (the source should
+    be pinned, see pinned_empty, and must stay untouched until the result is first used) so that it
+    overlaps with kernels already queued."""
+    host = np.asarray(host)
+    if blocking or host.ndim == 0 or runtime.world_size > 1:
+        return convert_to_cunumeric_ndarray(host)
+    return ndarray(shape=host.shape, dtype=host.dtype, thunk=DeferredArray.from_numpy_async(host))
+
+
+def map_chunks(fn, inputs, outputs, chunk: int) -> None:
+    """Out-of-core evaluation of an elementwise program over HOST arrays: `fn(*device_inputs)`
+    returns one device array per entry of `outputs`; the 1-D host `inputs` / `outputs` (ideally
+    pinned) are processed in chunks of `chunk` elements with the upload of chunk i+1, the kernels
+    of chunk i and the download of chunk i-1 in flight at the same time."""
+    n = inputs[0].shape[0]
+    starts = list(range(0, n, chunk))
+    pending: list = []
+
+    def upload(i):
+        s = starts[i]
+        return [from_host(a[s:s + chunk], blocking=False) for a in inputs]
+
+    nxt = upload(0)
+    for i, s in enumerate(starts):
+        cur = nxt
+        if i + 1 < len(starts):
+            nxt = upload(i + 1)
+        res = fn(*cur)
+        if not isinstance(res, (tuple, list)):
+            res = (res,)
+        pending.append([r.to_host(o[s:s + chunk], blocking=False) for r, o in zip(res, outputs)])
+        del res, cur
+        if len(pending) > 2:
+            for f in pending.pop(0):
+                f.wait()
+    for futs in pending:
+        for f in futs:
+            f.wait()
+
+
 def synchronize() -> None:
     runtime.synchronize()
 

@@ -19,12 +19,15 @@ from .config import argval_dtype, dtype_code
 class DeviceBuffer:
     """An owned, stream-ordered device allocation (freed back to the pool on GC)."""
 
-    __slots__ = ("ptr", "nbytes", "_runtime", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "_runtime", "ready_event", "__weakref__")
 
     def __init__(self, runtime: "Runtime", nbytes: int) -> None:
         self._runtime = runtime
         self.nbytes = int(nbytes)
         self.ptr = _lib.check_ptr(runtime.lib.cnb_malloc(max(self.nbytes, 1), runtime.stream))
+        # set while an asynchronous H2D copy (on the copy stream) is still filling this buffer; the
+        # compute stream waits for it the first time the buffer is used by a task
+        self.ready_event = None
 
     def __del__(self) -> None:
         try:
@@ -69,6 +72,9 @@ class Runtime:
         self.comm: Any = None
         self._scalar_cache: dict = {}
         self._argred_uids: dict = {}
+        self._h2d_stream: Any = None
+        self._d2h_stream: Any = None
+        self._event_pool: list = []
 
     # ------------------------------------------------------------------ lifecycle
     def ensure_initialized(self) -> None:
@@ -122,6 +128,55 @@ class Runtime:
         assert dst.flags.c_contiguous
         if dst.nbytes:
             _lib.check(self.lib.cnb_memcpy_d2h(dst.ctypes.data, src_ptr, dst.nbytes, self.stream))
+
+    # ------------------------------------------------------------------ asynchronous copies
+    # Separate copy streams let the H2D of the next batch, the kernels of the current one and the
+    # D2H of the previous one overlap (PCIe is full duplex).  Ordering is by events only.
+    def _copy_streams(self):
+        if self._h2d_stream is None:
+            self._h2d_stream = _lib.check_ptr(self.lib.cnb_stream_create())
+            self._d2h_stream = _lib.check_ptr(self.lib.cnb_stream_create())
+        return self._h2d_stream, self._d2h_stream
+
+    def _event(self):
+        return self._event_pool.pop() if self._event_pool else _lib.check_ptr(
+            self.lib.cnb_event_create())
+
+    def _recycle_event(self, ev) -> None:
+        self._event_pool.append(ev)
+
+    def copy_h2d_async(self, buf: DeviceBuffer, src: np.ndarray) -> None:
+        """Fill `buf` from (pinned) host memory on the H2D stream."""
+        assert src.flags.c_contiguous
+        h2d, _ = self._copy_streams()
+        # the pool handed out `buf` in compute-stream order: do not touch it before that point
+        ev = self._event()
+        _lib.check(self.lib.cnb_event_record(ev, self.stream))
+        _lib.check(self.lib.cnb_stream_wait_event(h2d, ev))
+        if src.nbytes:
+            _lib.check(self.lib.cnb_memcpy_h2d(buf.ptr, src.ctypes.data, src.nbytes, h2d))
+        _lib.check(self.lib.cnb_event_record(ev, h2d))
+        buf.ready_event = ev
+
+    def wait_ready(self, buf: DeviceBuffer) -> None:
+        ev = buf.ready_event
+        if ev is not None:
+            _lib.check(self.lib.cnb_stream_wait_event(self.stream, ev))
+            buf.ready_event = None
+            self._recycle_event(ev)
+
+    def copy_d2h_async(self, dst: np.ndarray, src_ptr: int):
+        """Start a D2H copy on the D2H stream once the compute stream reaches this point; returns
+        the event that marks its completion."""
+        assert dst.flags.c_contiguous
+        _, d2h = self._copy_streams()
+        ev = self._event()
+        _lib.check(self.lib.cnb_event_record(ev, self.stream))
+        _lib.check(self.lib.cnb_stream_wait_event(d2h, ev))
+        if dst.nbytes:
+            _lib.check(self.lib.cnb_memcpy_d2h(dst.ctypes.data, src_ptr, dst.nbytes, d2h))
+        _lib.check(self.lib.cnb_event_record(ev, d2h))
+        return ev
 
     def scalar_buffer(self, value: np.ndarray) -> DeviceBuffer:
         """Device copy of one scalar (the reference's Future-backed 0-d store); small LRU so that

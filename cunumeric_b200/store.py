@@ -156,6 +156,8 @@ class Store:
     def descriptor(self) -> _lib.cnb_store_t:
         if self.ndim > MAX_DIM:
             raise NotImplementedError(f"cunumeric_b200 supports at most {MAX_DIM} dimensions")
+        if self.buffer.ready_event is not None:
+            runtime.wait_ready(self.buffer)  # an asynchronous H2D copy is still filling it
         d = _lib.cnb_store_t()
         d.ptr = self.ptr
         d.dtype = dtype_code(self.dtype)

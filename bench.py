@@ -58,6 +58,23 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json): launch-weighted mean over its array-array and scalar-operand
+    launches.  None when no capture covers this kernel."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            data = json.load(f)
+        variants = data["kernels"][kernel]
+        n = sum(v["launches_per_step"] for v in variants.values())
+        total = sum((v["dram_read_bytes"] + v["dram_write_bytes"]) * v["launches_per_step"]
+                    for v in variants.values())
+        return total / n, "profiles/r01_traffic.json (ncu --set full, per launch)"
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md recipe).
     Uses NVML in a background thread (same counters as the recipe's nvidia-smi line, without
@@ -114,13 +131,21 @@ class ClockSampler:
                     sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                     power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
-                    self.samples.append((sm, reasons, power))
+                    self.samples.append((sm, reasons, power, time.perf_counter()))
                 except Exception as exc:  # keep sampling errors out of the measurement
                     self._err = str(exc)
                 self._stop.wait(self.period)
 
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
+
+    # The polling thread is started BEFORE the warm-up (the first NVML queries of a process are slow
+    # and contend with kernel launches); only samples taken inside [mark_begin, mark_end] count.
+    def mark_begin(self) -> None:
+        self._t0 = time.perf_counter()
+
+    def mark_end(self) -> None:
+        self._t1 = time.perf_counter()
 
     def stop(self) -> dict:
         if self._thread is None:
@@ -129,6 +154,10 @@ class ClockSampler:
         self._thread.join(timeout=2)
         import pynvml as nv
 
+        t0, t1 = getattr(self, "_t0", None), getattr(self, "_t1", None)
+        if t0 is not None and t1 is not None:
+            inside = [s for s in self.samples if t0 <= s[3] <= t1]
+            self.samples = inside or self.samples[-1:]
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self._max, "reasons": [self._err or "no samples"]}
         names = {
@@ -138,10 +167,10 @@ class ClockSampler:
             "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
             "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown,
         }
-        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r, _ in self.samples))
-        sm = [s for s, _, _ in self.samples]
+        reasons = sorted(n for n, bit in names.items() if any(s[1] & bit for s in self.samples))
+        sm = [s[0] for s in self.samples]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self._max, "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(p for _, _, p in self.samples)}
+                "samples": len(sm), "power_w_max": max(s[2] for s in self.samples)}
 
 
 def dist_setup(world: int):
@@ -307,23 +336,25 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
     S, X, T = cn.array(Sh), cn.array(Xh), cn.array(Th)
     cn.synchronize()
 
+    sampler = ClockSampler(cn.runtime.device)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         call, put = black_scholes(S, X, T, R, V)
     cn.synchronize()
 
     # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides
     ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
-    sampler = ClockSampler(cn.runtime.device)
     _lib.check(lib.cnb_trace_start(args.steps * (BLACK_SCHOLES_TASKS + 8)))
     barrier(dist)
-    sampler.start()
     cn.synchronize()
+    sampler.mark_begin()
     launches0 = cn.runtime.launch_count()
     lib.cnb_event_record(ev0, cn.runtime.stream)
     for _ in range(args.steps):
         call, put = black_scholes(S, X, T, R, V)
     lib.cnb_event_record(ev1, cn.runtime.stream)
     cn.synchronize()
+    sampler.mark_end()
     barrier(dist)
     launches = cn.runtime.launch_count() - launches0
     n_rec = lib.cnb_trace_stop()
@@ -338,6 +369,7 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
     if roofline is not None:
         roofline["peak_source"] = peak_src
         roofline.update(whole)
+        roofline["traffic"], roofline["traffic_source"] = load_traffic(roofline["kernel"])
 
     # ---- e2e: the same step through the public API from HOST buffers (pinned), copies inside
     e2e = None

@@ -25,22 +25,24 @@ def run_stencil(args, rank, world, dist, ClockSampler, load_peaks, max_over_rank
     lib = cn.runtime.lib
     peak_gbs, peak_src = load_peaks()
     grid = stencil_init(n, np.float64)
+    sampler = ClockSampler(cn.runtime.device)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         stencil_run(grid, iters)
     cn.synchronize()
 
     events = [lib.cnb_event_create() for _ in range(args.steps + 1)]
-    sampler = ClockSampler(cn.runtime.device)
     _lib.check(lib.cnb_trace_start(args.steps * iters * (STENCIL_TASKS_PER_ITER + 2)))
     barrier(dist)
-    sampler.start()
     cn.synchronize()
+    sampler.mark_begin()
     launches0 = cn.runtime.launch_count()
     lib.cnb_event_record(events[0], cn.runtime.stream)
     for i in range(args.steps):
         stencil_run(grid, iters)
         lib.cnb_event_record(events[i + 1], cn.runtime.stream)
     cn.synchronize()
+    sampler.mark_end()
     barrier(dist)
     launches = cn.runtime.launch_count() - launches0
     n_rec = lib.cnb_trace_stop()

@@ -40,7 +40,8 @@ struct EwPlan {
   long long tiles_per_row;
   long long num_tiles;
   int n_outer;
-  int vec;  // 1 = vector path legal for full tiles
+  int vec;      // 1 = vector path legal for full tiles
+  int out_pad;  // elements of slack per row for the store-alignment shift of the strided path
   EwOperand op[EW_MAX_OPS];  // outputs first, then inputs
 };
 
@@ -166,7 +167,13 @@ __device__ __forceinline__ void ew_load_one(Pack<T, 1>& r, const EwOperand& o, l
     ld_bytes<sizeof(T)>(r.raw, o.ptr + row_off + elem * o.inner_stride);
 }
 
-template <class Fn>
+// Two instantiations per functor, chosen by the launcher, so that neither path drags the other's
+// registers along (one combined kernel needed 76-141 registers once the strided path batched its
+// loads; capping it at 64 spilled in the vector path):
+//   VEC = true : plan.vec tasks — 128-bit path for full tiles, a plain element loop for the one
+//                ragged tile at the end of a row;
+//   VEC = false: everything else — the batched strided path.
+template <class Fn, bool VEC>
 __global__ void __launch_bounds__(EW_THREADS)
 ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
 {
@@ -206,7 +213,26 @@ ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
     }
     const long long col0 = ct * TILE;
 
-    if (plan.vec && col0 + TILE <= plan.inner) {
+    if constexpr (VEC) {
+      if (col0 + TILE > plan.inner) {
+        // ragged last tile of a row: one element per thread per step (all operands are
+        // inner-contiguous or broadcast here)
+        for (long long e = col0 + tid; e < plan.inner; e += EW_THREADS) {
+          Pack<I0, 1> a;
+          Pack<I1, 1> b;
+          Pack<I2, 1> c;
+          ew_load_one<I0>(a, plan.op[2], off[2], e);
+          ew_load_one<I1>(b, plan.op[3], off[3], e);
+          ew_load_one<I2>(c, plan.op[4], off[4], e);
+          Pack<O0, 1> r0;
+          Pack<O1, 1> r1;
+          fn(r0[0], r1[0], a[0], b[0], c[0]);
+          st_bytes<sizeof(O0)>(plan.op[0].ptr + off[0] + e * (long long)sizeof(O0), r0.raw);
+          if constexpr (HAS_O1)
+            st_bytes<sizeof(O1)>(plan.op[1].ptr + off[1] + e * (long long)sizeof(O1), r1.raw);
+        }
+        continue;
+      }
       // ---- 128-bit vector path: U independent chunk loads per operand, then compute + store
       Pack<I0, E> a[U];
       Pack<I1, E> b[U];
@@ -230,11 +256,20 @@ ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
           st_bytes<sizeof(O1) * E>(plan.op[1].ptr + off[1] + e * (long long)sizeof(O1), r1.raw);
       }
     } else {
-      // ---- strided / tail path: coalesced element accesses, batches of B independent loads
-      // independent loads per batch: ~128 bytes in flight per thread, like the vector path (a
-      // single-input kernel with 4 loads per batch ran at 53 % of the roofline: the stencil's COPY)
-      constexpr int B = S::in_bytes == 0 ? 8 : ew_cmax(4, ew_cmin(16, 128 / S::in_bytes));
+      // ---- strided path: coalesced element accesses, batches of B independent loads (~64 bytes
+      // in flight per thread)
+      constexpr int B = S::in_bytes == 0 ? 8 : ew_cmax(2, ew_cmin(16, 64 / S::in_bytes));
       constexpr int N = E * U;  // elements per thread per tile
+      // Shift the tile grid of this row so that warp stores start on a 128-byte line of the
+      // OUTPUT: a view whose rows start mid-sector (the stencil's `center[:] = work` lands 8 bytes
+      // past a sector) otherwise writes two partial sectors per warp store, which L2 can only
+      // complete with read-modify-write traffic (measured 56 % of the roofline for that COPY).
+      // Loads are indifferent to alignment.  ew_make_plan pads tiles_per_row for the shift.
+      long long shift = 0;
+      if (plan.out_pad != 0)
+        shift = static_cast<long long>(
+          (reinterpret_cast<unsigned long long>(plan.op[0].ptr + off[0]) & 127ull) / sizeof(O0));
+      const long long tbase = col0 - shift;
 #pragma unroll 1
       for (int j0 = 0; j0 < N; j0 += B) {
         Pack<I0, 1> a[B];
@@ -242,8 +277,8 @@ ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
         Pack<I2, 1> c[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-          const long long e = col0 + (long long)(j0 + j) * EW_THREADS + tid;
-          if (j0 + j < N && e < plan.inner) {
+          const long long e = tbase + (long long)(j0 + j) * EW_THREADS + tid;
+          if (j0 + j < N && e >= 0 && e < plan.inner) {
             ew_load_one<I0>(a[j], plan.op[2], off[2], e);
             ew_load_one<I1>(b[j], plan.op[3], off[3], e);
             ew_load_one<I2>(c[j], plan.op[4], off[4], e);
@@ -251,8 +286,8 @@ ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-          const long long e = col0 + (long long)(j0 + j) * EW_THREADS + tid;
-          if (j0 + j < N && e < plan.inner) {
+          const long long e = tbase + (long long)(j0 + j) * EW_THREADS + tid;
+          if (j0 + j < N && e >= 0 && e < plan.inner) {
             Pack<O0, 1> r0;
             Pack<O1, 1> r1;
             fn(r0[0], r1[0], a[j][0], b[j][0], c[j][0]);
@@ -266,7 +301,8 @@ ew_kernel(const __grid_constant__ EwPlan plan, const Fn fn)
   }
 }
 
-int ew_grid_size(const void* kernel, long long num_tiles);
+int ew_grid_size(const void* kernel, long long num_tiles, bool vec);
+int ew_grid_size(const void* kernel, long long num_tiles, int max_ctas_per_sm);
 // bytes the task must move: distinct elements touched per operand x itemsize (a stride-0 scalar
 // operand counts once) — the roofline numerator of SURVEY §8(d)
 long long ew_algorithmic_bytes(const EwPlan& plan, const EwArg* args, int nargs);
@@ -287,8 +323,8 @@ int ew_launch(const Fn& fn, const cnb_store_t* o0, const cnb_store_t* o1, const 
   EwPlan plan;
   int rc = ew_make_plan(plan, args, EW_MAX_OPS, chunk, S::TILE);
   if (rc <= 0) return rc;
-  auto kernel = ew_kernel<Fn>;
-  int grid    = ew_grid_size(reinterpret_cast<const void*>(kernel), plan.num_tiles);
+  auto kernel = plan.vec ? ew_kernel<Fn, true> : ew_kernel<Fn, false>;
+  int grid    = ew_grid_size(reinterpret_cast<const void*>(kernel), plan.num_tiles, plan.vec != 0);
   {
     LaunchScope scope(stream, KERNEL_ELEMENTWISE, plan.inner * plan.rows,
                       ew_algorithmic_bytes(plan, args, EW_MAX_OPS));

@@ -2,6 +2,7 @@
 #include "cnb_elementwise.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -130,8 +131,14 @@ int ew_make_plan(EwPlan& plan, const EwArg* args, int nargs, const int* chunk_by
     for (int d = 0; d < EW_MAX_OUTER; ++d)
       if (o.outer_stride[d] % align != 0) vec = false;
   }
-  plan.vec           = vec ? 1 : 0;
-  plan.tiles_per_row = (plan.inner + tile_elems - 1) / tile_elems;
+  plan.vec = vec ? 1 : 0;
+  // strided path: rows may be shifted by up to one 128-byte line of the output so that warp
+  // stores are line-aligned (see ew_kernel); reserve the slack
+  plan.out_pad = 0;
+  if (!vec && args[0].store != nullptr && args[0].is_output &&
+      plan.op[0].inner_stride == args[0].itemsize && args[0].itemsize < 128)
+    plan.out_pad = 128 / args[0].itemsize - 1;
+  plan.tiles_per_row = (plan.inner + plan.out_pad + tile_elems - 1) / tile_elems;
   plan.num_tiles     = plan.tiles_per_row * plan.rows;
   return 1;
 }
@@ -149,7 +156,23 @@ long long ew_algorithmic_bytes(const EwPlan& plan, const EwArg* args, int nargs)
   return total;
 }
 
-int ew_grid_size(const void* kernel, long long num_tiles)
+int ew_grid_size(const void* kernel, long long num_tiles, int max_ctas_per_sm);
+
+int ew_grid_size(const void* kernel, long long num_tiles, bool vec)
+{
+  static const int forced = [] {
+    const char* e = getenv("CNB_EW_CTAS_PER_SM");
+    return e ? atoi(e) : 0;
+  }();
+  // Fewer, fatter CTAs stream better: with ~128 bytes of loads in flight per thread a couple of
+  // resident CTAs per SM already cover the HBM latency, and more concurrent tile streams only add
+  // DRAM page conflicts.  Measured on B200 (profiles/r01_ctas_per_sm.md): the 128-bit kernels peak
+  // at 2 CTAs/SM (94.8 % of the roofline on Black-Scholes; 92.8 % at 3, 89.7 % at 4+), the strided
+  // kernels at 3 (92.5 % on the stencil; 81 % at 2, 90.9 % at 4).  CNB_EW_CTAS_PER_SM overrides.
+  return ew_grid_size(kernel, num_tiles, forced > 0 ? forced : (vec ? 2 : 3));
+}
+
+int ew_grid_size(const void* kernel, long long num_tiles, int max_ctas_per_sm)
 {
   // persistent CTAs: SMs x resident CTAs per SM (queried once per kernel)
   static std::mutex mu;
@@ -167,6 +190,7 @@ int ew_grid_size(const void* kernel, long long num_tiles)
     std::lock_guard<std::mutex> g(mu);
     cache[kernel] = per_sm;
   }
+  per_sm = std::min(per_sm, max_ctas_per_sm);
   long long resident = static_cast<long long>(sm_count()) * per_sm;
   return static_cast<int>(std::max<long long>(1, std::min<long long>(num_tiles, resident)));
 }

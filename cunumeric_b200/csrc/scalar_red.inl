@@ -202,7 +202,7 @@ int scalar_red_by_type(const cnb_store_t* out, const cnb_store_t* in, const cnb_
       rc = red_acquire_scratch(scratch, stream);
       if (rc != CNB_OK) return rc;
       auto kernel = scalar_red_kernel<R>;
-      int grid    = ew_grid_size(reinterpret_cast<const void*>(kernel), plan.num_tiles);
+      int grid    = ew_grid_size(reinterpret_cast<const void*>(kernel), plan.num_tiles, 32);
       if (grid > scratch.max_grid) grid = scratch.max_grid;
       {
         LaunchScope scope(stream, KERNEL_SCALAR_RED, plan.inner * plan.rows,

@@ -17,14 +17,17 @@ from .config import argval_dtype, dtype_code
 
 
 class DeviceBuffer:
-    """An owned, stream-ordered device allocation (freed back to the pool on GC)."""
+    """An owned device allocation.  Blocks come from a size-keyed free list kept by the runtime
+    (every task runs on the single compute stream, so a block released by Python's reference
+    counting can be handed out again immediately: stream order already serialises the old reader
+    and the new writer); misses go to the stream-ordered CUDA pool."""
 
-    __slots__ = ("ptr", "nbytes", "_runtime", "ready_event", "__weakref__")
+    __slots__ = ("ptr", "base", "nbytes", "_runtime", "ready_event", "__weakref__")
 
     def __init__(self, runtime: "Runtime", nbytes: int) -> None:
         self._runtime = runtime
-        self.nbytes = int(nbytes)
-        self.ptr = _lib.check_ptr(runtime.lib.cnb_malloc(max(self.nbytes, 1), runtime.stream))
+        self.nbytes = max(int(nbytes), 1)
+        self.base, self.ptr = runtime._take_block(self.nbytes)
         # set while an asynchronous H2D copy (on the copy stream) is still filling this buffer; the
         # compute stream waits for it the first time the buffer is used by a task
         self.ready_event = None
@@ -33,7 +36,7 @@ class DeviceBuffer:
         try:
             rt = self._runtime
             if rt is not None and rt.lib is not None and self.ptr:
-                rt.lib.cnb_free(self.ptr, rt.stream)
+                rt._give_block(self.base, self.ptr, self.nbytes)
         except Exception:
             pass
         self.ptr = None
@@ -75,6 +78,10 @@ class Runtime:
         self._h2d_stream: Any = None
         self._d2h_stream: Any = None
         self._event_pool: list = []
+        self._free_blocks: dict = {}
+        self._cached_bytes = 0
+        self._cache_limit = None
+        self._colour = 0
 
     # ------------------------------------------------------------------ lifecycle
     def ensure_initialized(self) -> None:
@@ -112,6 +119,49 @@ class Runtime:
     def allocate(self, nbytes: int) -> DeviceBuffer:
         self.ensure_initialized()
         return DeviceBuffer(self, nbytes)
+
+    # Large blocks are "coloured": each gets a different sub-2-MiB start offset, so that the
+    # operands of one task are never congruent modulo a large power of two.  Power-of-two sized
+    # arrays laid out back to back otherwise walk the same L2 slices / HBM channels in lock step
+    # (measured: WHERE on 2^30 fp16 elements dropped from 93 % to 58 % of the roofline).
+    _COLOUR_MIN = 32 << 20
+    _COLOUR_SPAN = 2 << 20
+
+    def _take_block(self, nbytes: int):
+        blocks = self._free_blocks.get(nbytes)
+        if blocks:
+            self._cached_bytes -= nbytes
+            return blocks.pop()
+        pad = self._COLOUR_SPAN if nbytes >= self._COLOUR_MIN else 0
+        base = self.lib.cnb_malloc(nbytes + pad, self.stream)
+        if not base and self._cached_bytes:
+            self.release_cached_memory()  # out of memory: give the cached blocks back and retry
+            base = self.lib.cnb_malloc(nbytes + pad, self.stream)
+        base = _lib.check_ptr(base)
+        offset = 0
+        if pad:
+            self._colour = (self._colour + 1) % 61
+            offset = (self._colour * 33792) % pad & ~511  # 33 KiB steps, 512-byte aligned
+        return base, base + offset
+
+    def _give_block(self, base: int, ptr: int, nbytes: int) -> None:
+        if self._cache_limit is None:
+            free, total = ctypes.c_size_t(), ctypes.c_size_t()
+            self.lib.cnb_mem_info(ctypes.byref(free), ctypes.byref(total))
+            self._cache_limit = int(0.5 * total.value)
+        if self._cached_bytes + nbytes > self._cache_limit:
+            self.lib.cnb_free(base, self.stream)
+            return
+        self._free_blocks.setdefault(nbytes, []).append((base, ptr))
+        self._cached_bytes += nbytes
+
+    def release_cached_memory(self) -> None:
+        """Return every cached block to the CUDA pool."""
+        for blocks in self._free_blocks.values():
+            for base, _ in blocks:
+                self.lib.cnb_free(base, self.stream)
+        self._free_blocks.clear()
+        self._cached_bytes = 0
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
         self.ensure_initialized()

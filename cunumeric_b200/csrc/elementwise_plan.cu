@@ -164,12 +164,14 @@ int ew_grid_size(const void* kernel, long long num_tiles, bool vec)
     const char* e = getenv("CNB_EW_CTAS_PER_SM");
     return e ? atoi(e) : 0;
   }();
-  // Fewer, fatter CTAs stream better: with ~128 bytes of loads in flight per thread a couple of
-  // resident CTAs per SM already cover the HBM latency, and more concurrent tile streams only add
-  // DRAM page conflicts.  Measured on B200 (profiles/r01_ctas_per_sm.md): the 128-bit kernels peak
-  // at 2 CTAs/SM (94.8 % of the roofline on Black-Scholes; 92.8 % at 3, 89.7 % at 4+), the strided
-  // kernels at 3 (92.5 % on the stencil; 81 % at 2, 90.9 % at 4).  CNB_EW_CTAS_PER_SM overrides.
-  return ew_grid_size(kernel, num_tiles, forced > 0 ? forced : (vec ? 2 : 3));
+  // Fewer, fatter CTAs stream better: with ~128 bytes of loads in flight per thread a few resident
+  // CTAs per SM already cover the HBM latency, and more concurrent tile streams only add DRAM page
+  // conflicts.  Measured on B200 (profiles/r01_ctas_per_sm.md): 3 CTAs/SM is within 2-3 % of the
+  // best setting for every kernel variant tried (2 is slightly better for some fp32/fp64 kernels
+  // but costs 15-20 % on WHERE fp16/fp64 and scalar-operand fp16; 4+ loses 2-5 % across the board).
+  // CNB_EW_CTAS_PER_SM overrides.
+  (void)vec;
+  return ew_grid_size(kernel, num_tiles, forced > 0 ? forced : 3);
 }
 
 int ew_grid_size(const void* kernel, long long num_tiles, int max_ctas_per_sm)

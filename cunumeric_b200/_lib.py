@@ -53,6 +53,7 @@ PROTOTYPES = {
     "cnb_convert": (_i32, [_i32, _store_p, _store_p, _vp]),
     "cnb_scalar_unary_red": (_i32, [_i32, _store_p, _store_p, _store_p, _vp, _vp, _vp, _vp]),
     "cnb_unary_red": (_i32, [_i32, _i32, _store_p, _store_p, _store_p, _i64, _vp]),
+    "cnb_binary_red": (_i32, [_i32, _store_p, _store_p, _store_p, _vp, _vp]),
     "cnb_fill": (_i32, [_store_p, _vp, _vp]),
     "cunumeric_perform_registration": (None, []),
     "cunumeric_has_curand": (_i32, []),

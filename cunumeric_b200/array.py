@@ -495,6 +495,21 @@ class ndarray:
         return out
 
     @classmethod
+    def _perform_binary_reduction(cls, op, one: "ndarray", two: "ndarray", dtype,
+                                  extra_args=None) -> "ndarray":
+        """array.py:4420-4452."""
+        assert dtype is not None and np.dtype(dtype) == np.bool_
+        broadcast = None
+        if one.shape != two.shape:
+            broadcast = np.broadcast_shapes(one.shape, two.shape)
+        common_type = cls.find_common_type(one, two)
+        one_thunk = one._maybe_convert(common_type)._thunk
+        two_thunk = two._maybe_convert(common_type)._thunk
+        dst = ndarray(shape=(), dtype=np.bool_)
+        dst._thunk.binary_reduction(op, one_thunk, two_thunk, broadcast, extra_args or ())
+        return dst
+
+    @classmethod
     def _perform_where(cls, mask: "ndarray", one: "ndarray", two: "ndarray") -> "ndarray":
         """array.py:4455-4470."""
         args = (mask, one, two)

@@ -30,6 +30,8 @@ int unary_getarg(const cnb_store_t*, const cnb_store_t*, cudaStream_t);
 int where_select(const cnb_store_t*, const cnb_store_t*, const cnb_store_t*, const cnb_store_t*,
                  cudaStream_t);
 int fill_value(const cnb_store_t*, const void*, cudaStream_t);
+int binary_red(int, const cnb_store_t*, const cnb_store_t*, const cnb_store_t*, const void*,
+               cudaStream_t);
 
 namespace {
 int check_store(const cnb_store_t* s, const char* name)
@@ -165,6 +167,18 @@ int cnb_unary_red(int32_t op, int32_t axis, const cnb_store_t* out, const cnb_st
   if (op == CNB_RED_CONTAINS)
     return set_error(CNB_ERR_INVALID_OP, "CONTAINS exists on the scalar path only");
   return set_error(CNB_ERR_BAD_ARG, "unknown reduction opcode %d", op);
+}
+
+int cnb_binary_red(int32_t op, const cnb_store_t* out, const cnb_store_t* in1,
+                   const cnb_store_t* in2, const void* extra, void* stream)
+{
+  CNB_CHECK(ensure_init());
+  CNB_CHECK(check_store(out, "out"));
+  CNB_CHECK(check_store(in1, "in1"));
+  CNB_CHECK(check_store(in2, "in2"));
+  if (in1->dtype >= CNB_NUM_DTYPES) return set_error(CNB_ERR_BAD_ARG, "BINARY_RED on a struct dtype");
+  set_task_tag(CNB_OP_BINARY_RED, op, in1->dtype);
+  return binary_red(op, out, in1, in2, extra, (cudaStream_t)stream);
 }
 
 int cnb_fill(const cnb_store_t* out, const void* value, void* stream)

@@ -256,6 +256,30 @@ class DeferredArray:
         assert not equal_nan
         self.binary_op(BinaryOpCode.ISCLOSE, rhs1, rhs2, True, (rtol, atol))
 
+    # ------------------------------------------------------------------ BINARY_RED
+    def binary_reduction(self, op: BinaryOpCode, src1: "DeferredArray", src2: "DeferredArray",
+                         broadcast: Any, args: Sequence[Any]) -> None:
+        """deferred.py:3330-3364: `self` (a bool scalar) <- all(op(src1, src2))."""
+        if hasattr(src1, "gather") or hasattr(src2, "gather"):
+            from .distributed import partitioned_binary_reduction
+
+            if partitioned_binary_reduction(self, op, src1, src2, broadcast, args):
+                return
+        src1, src2 = _rep(src1), _rep(src2)
+        rhs1, rhs2 = src1.base, src2.base
+        if broadcast is not None:
+            rhs1, rhs2 = rhs1.broadcast_to(broadcast), rhs2.broadcast_to(broadcast)
+        self.fill(np.array(True))
+        lhs = self.base
+        while lhs.ndim > 1:
+            lhs = lhs.project(0, 0)
+        if lhs.ndim == 0:
+            lhs = lhs.promote(0, 1)
+        extra = _host_scalars(args, np.float64) if op == BinaryOpCode.ISCLOSE else None
+        d_out, d1, d2 = lhs.descriptor(), rhs1.descriptor(), rhs2.descriptor()
+        _lib.check(runtime.lib.cnb_binary_red(int(op), ctypes.byref(d_out), ctypes.byref(d1),
+                                              ctypes.byref(d2), _vp(extra), runtime.stream))
+
     # ------------------------------------------------------------------ WHERE
     def where(self, mask: "DeferredArray", one: "DeferredArray", two: "DeferredArray") -> None:
         lhs = self.base

@@ -527,6 +527,39 @@ def _allreduce(partial: DeferredArray, op: UnaryRedCode, argred: bool, elem: np.
     return out
 
 
+def partitioned_binary_reduction(lhs: DeferredArray, op: BinaryOpCode, src1: Any, src2: Any,
+                                 broadcast: Any, args: Any) -> bool:
+    """BINARY_RED over row-partitioned operands: every rank folds its own rows into a local bool
+    (the point tasks of deferred.py:3330-3364), the bools are ANDed across ranks (the
+    ProdReduction<bool> the reference's runtime applies to the scalar result).  Returns False when
+    the operands cannot be aligned row for row (the caller then gathers)."""
+    lead = src1 if isinstance(src1, PartitionedArray) else src2
+    shape = tuple(broadcast) if broadcast is not None else lead.shape
+    if lead.shape != shape or lead.ndim == 0:
+        return False
+    vlo, vhi = lead.owned
+    ops = []
+    for s in (src1, src2):
+        if s is lead:
+            ops.append(None)
+        elif isinstance(s, PartitionedArray):
+            if s.shape != shape:
+                return False
+            ops.append(lead._operand(s, vlo, vhi))  # collective (row fetch) if misaligned
+        else:
+            cut = s.base.broadcast_to(shape) if s.shape != shape else s.base
+            ops.append(DeferredArray(cut.slice(0, slice(vlo, vhi))))
+    partial = DeferredArray(Store.empty((1,), np.bool_))
+    partial.fill(np.array(True))
+    if vhi > vlo:
+        mine = lead.local_rows(vlo, vhi)
+        a, b = [mine if o is None else o for o in ops]
+        partial.binary_reduction(op, a, b, None, args)
+    _nccl_allreduce(partial, UnaryRedCode.ALL)
+    lhs.copy(DeferredArray(partial.base.reshape_contiguous(lhs.shape)), deep=True)
+    return True
+
+
 def _assign_any(lhs: Any, src: Any) -> None:
     if isinstance(lhs, PartitionedArray):
         lhs.copy(src)

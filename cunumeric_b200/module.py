@@ -279,6 +279,29 @@ def clip(a, a_min, a_max, out=None):
     return convert_to_cunumeric_ndarray(a).clip(a_min, a_max, out=out)
 
 
+def array_equal(a1, a2, equal_nan: bool = False):
+    """module.py:5337-5375 -> BINARY_RED(EQUAL)."""
+    from .config import BinaryOpCode
+
+    if equal_nan:
+        raise NotImplementedError("cuNumeric does not support `equal_nan` yet for `array_equal`")
+    a1, a2 = convert_to_cunumeric_ndarray(a1), convert_to_cunumeric_ndarray(a2)
+    if a1.shape != a2.shape:
+        return False
+    return ndarray._perform_binary_reduction(BinaryOpCode.EQUAL, a1, a2, np.dtype(np.bool_))
+
+
+def allclose(a, b, rtol=1e-5, atol=1e-8, equal_nan: bool = False):
+    """module.py `allclose` -> BINARY_RED(ISCLOSE) with rtol/atol as extra scalars."""
+    from .config import BinaryOpCode
+
+    if equal_nan:
+        raise NotImplementedError("cuNumeric does not support `equal_nan` yet for allclose")
+    a, b = convert_to_cunumeric_ndarray(a), convert_to_cunumeric_ndarray(b)
+    return ndarray._perform_binary_reduction(BinaryOpCode.ISCLOSE, a, b, np.dtype(np.bool_),
+                                             extra_args=(rtol, atol))
+
+
 def isclose(a, b, rtol=1e-5, atol=1e-8, equal_nan=False) -> ndarray:
     """module.py `isclose` -> BINARY_OP(ISCLOSE) with rtol/atol as extra scalars."""
     if equal_nan:

@@ -182,6 +182,13 @@ int cnb_scalar_unary_red(int32_t op, const cnb_store_t* out, const cnb_store_t* 
 int cnb_unary_red(int32_t op, int32_t axis, const cnb_store_t* out, const cnb_store_t* in,
                   const cnb_store_t* where, int64_t axis_origin, void* stream);
 
+/* BINARY_RED — replaces BinaryRedTask::gpu_variant (src/cunumeric/binary/binary_red.cu:105-108;
+ * contract deferred.py:3330-3364 <-> binary_red_template.inl:31-75): array_equal / allclose.
+ * op is CNB_BINOP_EQUAL or CNB_BINOP_ISCLOSE (extra = host double[2] {rtol, atol}); out is a
+ * 1-element CNB_BOOL store pre-filled with true, and is set to false if any pair fails. */
+int cnb_binary_red(int32_t op, const cnb_store_t* out, const cnb_store_t* in1,
+                   const cnb_store_t* in2, const void* extra, void* stream);
+
 /* FILL — replaces FillTask::gpu_variant (src/cunumeric/nullary/fill.cu; deferred.py:1463-1496).
  * value: host pointer to one element of out's dtype (Argval fill: 16 bytes). */
 int cnb_fill(const cnb_store_t* out, const void* value, void* stream);

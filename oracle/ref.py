@@ -81,6 +81,7 @@ def lib():
         vp, i32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
         L.ref_binary_out_code.argtypes = [i32, i32]
         L.ref_binary_op.argtypes = [i32, i32, vp, vp, vp, sz, vp, i32]
+        L.ref_binary_red.argtypes = [i32, i32, vp, vp, vp, sz, vp]
         L.ref_binary_op_strided.argtypes = [i32, i32, vp, sz, vp, sz, vp, sz, vp, i32]
         L.ref_unary_out_code.argtypes = [i32, i32]
         L.ref_unary_op.argtypes = [i32, i32, vp, vp, sz, vp, i32]
@@ -139,6 +140,21 @@ def binary_op(op: str, a, b, rtol: float = 1e-5, atol: float = 1e-8, nthreads: i
                              _ptr(extra), nthreads)
     assert rc == CODE_OF[odt], rc
     return out
+
+
+def binary_red(op: str, a, b, rtol: float = 1e-5, atol: float = 1e-8) -> bool:
+    """BINARY_RED: all(op(a, b)) for op in EQUAL / ISCLOSE (binary/binary_red.cc:38-47)."""
+    a = _dense(a)
+    b = _dense(b, a.dtype)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    out = np.array([True])
+    extra = np.array([rtol, atol], dtype=np.float64)
+    rc = lib().ref_binary_red(BINARY[op], CODE_OF[a.dtype], _ptr(a), _ptr(b), _ptr(out), a.size,
+                              _ptr(extra))
+    if rc == ERR_INVALID:
+        raise InvalidOp(f"{op}/{a.dtype}")
+    assert rc == 0, rc
+    return bool(out[0])
 
 
 def binary_op_bcast(op: str, a, b, nthreads: int = 1, out=None):

@@ -72,9 +72,52 @@ int dispatch(int op, int code, const void* a, const void* b, void* o, size_t n,
   return ref::ERR_BADCODE;
 }
 
+// BINARY_RED: the dense CPU body of binary/binary_red.cc:38-47 — early exit on the first failing
+// pair, result folded into `out` with ProdReduction<bool> (out &= result).
+template <BinaryOpCode OP, Code CODE>
+int run_red(const void* in1v, const void* in2v, bool* out, size_t n, const double* extra)
+{
+  if constexpr (!BinaryOp<OP, CODE>::valid) {
+    return ref::ERR_INVALID;
+  } else {
+    using FN  = BinaryOp<OP, CODE>;
+    using ARG = legate::legate_type_of<CODE>;
+    std::vector<legate::Store> args;
+    if (OP == BinaryOpCode::ISCLOSE) {
+      args.emplace_back(&extra[0]);
+      args.emplace_back(&extra[1]);
+    }
+    FN func{args};
+    auto in1 = static_cast<const ARG*>(in1v);
+    auto in2 = static_cast<const ARG*>(in2v);
+    for (size_t idx = 0; idx < n; ++idx)
+      if (!func(in1[idx], in2[idx])) {
+        *out = *out && false;
+        return 0;
+      }
+    *out = *out && true;
+    return 0;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// *out &= all(op(in1[i], in2[i])); op must be EQUAL or ISCLOSE (binary_op_util.h reduce_op_dispatch)
+int ref_binary_red(int op, int code, const void* in1, const void* in2, bool* out, size_t n,
+                   const double* extra)
+{
+  return ref::type_dispatch(code, [&](auto tag) {
+    constexpr Code CODE = decltype(tag)::value;
+    switch (static_cast<BinaryOpCode>(op)) {
+      case BinaryOpCode::EQUAL: return run_red<BinaryOpCode::EQUAL, CODE>(in1, in2, out, n, extra);
+      case BinaryOpCode::ISCLOSE:
+        return run_red<BinaryOpCode::ISCLOSE, CODE>(in1, in2, out, n, extra);
+      default: return static_cast<int>(ref::ERR_BADCODE);
+    }
+  });
+}
 
 // Returns the dtype code of the result the reference functor produces, or <0.
 int ref_binary_out_code(int op, int code)

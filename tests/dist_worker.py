@@ -76,6 +76,18 @@ def main() -> None:
     assert int(V.sum()) == int(v.sum()) and int(V.argmax()) == int(v.argmax())
     assert float(X.sum(initial=10.0)) == pytest_approx(x.sum(dtype=np.float64) + 10.0)
 
+    # ---- BINARY_RED: local fold per row block + AND across ranks
+    Y = cn.array(x.copy())
+    assert isinstance(Y._thunk, PartitionedArray)
+    assert bool(cn.array_equal(X, Y)) and bool(cn.allclose(X, Y))
+    assert bool(cn.array_equal(X, x)) and bool(cn.allclose(X, cn.array(x[0]) * 0 + X))
+    Y[202, 63] = 1e9  # a single mismatch owned by the last rank only
+    assert not bool(cn.array_equal(X, Y)) and not bool(cn.allclose(X, Y))
+    Y[202, 63] = float(x[202, 63])
+    Y[0, 0] = 1e9  # ... and by the first rank only
+    assert not bool(cn.array_equal(X, Y))
+    assert bool(cn.array_equal(X[1:-1], Y[1:-1]))  # shifted views: row fetch then local fold
+
     cn.synchronize()
     dist.barrier()
     dist.destroy_process_group()

@@ -85,11 +85,12 @@ def main() -> None:
     ap.add_argument("--c3", action="store_true")
     ap.add_argument("--c5", action="store_true")
     ap.add_argument("--cvt", action="store_true")
+    ap.add_argument("--fill", action="store_true", help="write-only / read-only ceilings")
     ap.add_argument("--log2n", type=int, default=30)
     ap.add_argument("--rows", type=int, default=32768)
     ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
-    if not (args.c3 or args.c5 or args.cvt):
+    if not (args.c3 or args.c5 or args.cvt or args.fill):
         args.c3 = args.c5 = True
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -128,6 +129,22 @@ def main() -> None:
             sec = timer.run(lambda: a.astype(dst), args.reps)
             report(rank, world, f"C5 astype {name}->{dst.name}", n, s + dst.itemsize, sec, peak)
             del a
+
+    if args.fill:
+        # context for write-heavy kernels: a pure store stream (FILL), a 1:1 copy and a pure load
+        # stream (scalar SUM) — the measured "peak" in MEASURED_PEAKS.json is a 1:1 copy
+        n = 1 << args.log2n
+        for name, dt in (("float32", np.float32), ("float64", np.float64), ("int8", np.int8)):
+            s = np.dtype(dt).itemsize
+            a = cn.empty((n,), dtype=dt)
+            sec = timer.run(lambda: a.fill(1), args.reps)
+            report(rank, world, f"FILL {name} (write only)", n, s, sec, peak)
+            b = cn.empty((n,), dtype=dt)
+            sec = timer.run(lambda: b._thunk.copy(a._thunk, deep=True), args.reps)
+            report(rank, world, f"COPY {name} (1:1)", n, 2 * s, sec, peak)
+            sec = timer.run(lambda: a.sum(), args.reps)
+            report(rank, world, f"SUM {name} (read only)", n, s, sec, peak)
+            del a, b
 
     if args.cvt:
         # every CONVERT pair (14 x 13) — hunts for conversion instructions that issue slowly

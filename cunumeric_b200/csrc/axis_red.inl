@@ -13,9 +13,11 @@
 //     rows) per output element, 128-bit loads along the axis, shuffle + shared-memory fold.
 // Results are folded into the caller's pre-filled output store (reduce-accessor semantics).
 #include "cnb_reduce.cuh"
+#include "cnb_tma.cuh"
 #include "ops_reduce.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace cnb {
 
@@ -363,6 +365,167 @@ axis_row_kernel(const __grid_constant__ AxisPlan p, const R r)
   }
 }
 
+// ROW mode, long contiguous rows: bulk-copy (TMA) pipeline.  ROWT_CTAS_PER_SM persistent CTAs per
+// SM; warp 8's elected lane streams every row of the CTA through a ring of ROWT_STAGES x ROWT_CHUNK
+// bytes of shared memory with cp.async.bulk, the 8 consumer warps fold the chunks out of shared
+// memory.  The producer runs up to a full ring ahead, so HBM stays busy while the consumers do the
+// cross-warp fold and the store of a finished row — the bubble that holds the plain LDG kernel
+// at ~90 % of the copy roofline.  Three CTAs per SM (192 KB of ring in total) rather than one fat
+// one, so that the row epilogue of one CTA — ~250 dependent instructions for an arg-reduction —
+// overlaps the folding done by the other two (one CTA per SM: SUM 104 %, ARGMAX 62 %).  Requirements (checked by the launcher): contiguous axis, no mask,
+// 16-byte aligned base / row pitch / row length.
+constexpr int ROWT_CONSUMERS = RED_THREADS;
+constexpr int ROWT_THREADS   = RED_THREADS + 32;
+constexpr int ROWT_STAGES    = 4;
+constexpr int ROWT_CTAS_PER_SM = 3;
+constexpr int ROWT_CHUNK     = 16384;
+constexpr int ROWT_SMEM      = ROWT_STAGES * ROWT_CHUNK + 1024;
+
+template <class R>
+__global__ void __launch_bounds__(ROWT_THREADS, ROWT_CTAS_PER_SM)
+axis_row_tma_kernel(const __grid_constant__ AxisPlan p, const R r)
+{
+  using T   = typename R::In;
+  using Acc = typename R::Acc;
+  using Val = typename R::Val;
+  constexpr int V = (16 / sizeof(T)) < 1 ? 1 : 16 / sizeof(T);
+  static_assert(sizeof(T) * V == 16, "one 128-bit shared-memory load per step");
+  extern __shared__ __align__(1024) unsigned char rowt_smem[];
+  // [ring | full barriers | empty barriers | cross-warp partials (2 x 8 Acc)]
+  unsigned char* ring = rowt_smem;
+  uint64_t* bars      = reinterpret_cast<uint64_t*>(rowt_smem + ROWT_STAGES * ROWT_CHUNK);
+  Acc* partials       = reinterpret_cast<Acc*>(rowt_smem + ROWT_STAGES * ROWT_CHUNK + 256);
+  static_assert(2 * RED_WARPS * sizeof(Acc) <= 768, "partials fit behind the barriers");
+  const uint32_t full0  = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + ROWT_STAGES);
+  const uint32_t ring0  = smem_u32(ring);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ROWT_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);           // one arrive.expect_tx by the producer
+      mbar_init(empty0 + 8 * s, RED_WARPS);  // one arrive per consumer warp
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long row_bytes = p.alen * (long long)sizeof(T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int stage      = 0;
+  uint32_t phase = 0;
+
+  if (warp == RED_WARPS) {
+    // ---- producer
+    if (lane != 0) return;
+    for (long long c = blockIdx.x; c < p.ncols; c += gridDim.x) {
+      long long q        = c;
+      const long long k2 = q % p.kept[2];
+      q /= p.kept[2];
+      const long long k1 = q % p.kept[1];
+      const long long k0 = q / p.kept[1];
+      const char* src    = p.in + k0 * p.in_k[0] + k1 * p.in_k[1] + k2 * p.in_k[2];
+      for (long long off = 0; off < row_bytes; off += ROWT_CHUNK) {
+        const uint32_t nb = (uint32_t)min((long long)ROWT_CHUNK, row_bytes - off);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1u);  // passes at once on a fresh barrier
+        mbar_arrive_expect_tx(full0 + 8 * stage, nb);
+        bulk_g2s(ring0 + stage * ROWT_CHUNK, src + off, nb, full0 + 8 * stage);
+        if (++stage == ROWT_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int tid = threadIdx.x;
+  int parity    = 0;
+  for (long long c = blockIdx.x; c < p.ncols; c += gridDim.x) {
+    // UNR independent accumulator chains per thread: the fold of one element must not wait for
+    // the previous one (with 8 consumer warps per SM a single dependent chain made ARGMAX
+    // latency-bound at 64 % of the roofline).  Every chain sees increasing indices.
+    constexpr int UNR = ROWT_CHUNK / 16 / ROWT_CONSUMERS;  // 4
+    Acc a[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) a[u] = R::identity();
+    for (long long off = 0; off < row_bytes; off += ROWT_CHUNK) {
+      const int nvec = (int)(min((long long)ROWT_CHUNK, row_bytes - off) >> 4);
+      mbar_wait(full0 + 8 * stage, phase);
+      const char* buf    = reinterpret_cast<const char*>(ring) + stage * ROWT_CHUNK;
+      const long long e0 = p.axis_origin + off / (long long)sizeof(T);
+      if (nvec == ROWT_CHUNK / 16) {
+        Pack<T, V> x[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) ld_bytes<16>(x[u].raw, buf + (u * ROWT_CONSUMERS + tid) * 16);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+            red_visit(r, a[u], x[u][v], true,
+                      [&] { return e0 + ((u * ROWT_CONSUMERS + tid) * V + v); });
+      } else {
+        for (int i = tid; i < nvec; i += ROWT_CONSUMERS) {
+          Pack<T, V> x;
+          ld_bytes<16>(x.raw, buf + i * 16);
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            red_visit(r, a[0], x[v], true, [&] { return e0 + (i * V + v); });
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+      if (++stage == ROWT_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    // chains hold interleaved index sets: the general (tie-breaking) fold merges them
+    Acc acc = R::fold(R::fold(a[0], a[1]), R::fold(a[2], a[3]));
+    static_assert(UNR == 4, "chain merge above is written for 4 chains");
+    // fold the row across the 8 consumer warps; partials are double-buffered by row parity so one
+    // named barrier per row is enough (a warp can only overwrite buffer b after passing the NEXT
+    // row's barrier, which warp 0 reaches after it has read b)
+    acc      = warp_reduce<R>(acc);
+    Acc* buf = partials + parity * RED_WARPS;
+    if (lane == 0) buf[warp] = acc;
+    named_bar_sync(1, ROWT_CONSUMERS);
+    if (warp == 0) {
+      Acc t = (lane < RED_WARPS) ? buf[lane] : R::identity();
+#pragma unroll
+      for (int m = RED_WARPS / 2; m > 0; m >>= 1) {
+        Acc o = shfl_xor_any(t, m);
+        t     = ((lane & m) == 0) ? R::fold(t, o) : R::fold(o, t);
+      }
+      if (lane == 0) {
+        long long q        = c;
+        const long long k2 = q % p.kept[2];
+        q /= p.kept[2];
+        const long long k1 = q % p.kept[1];
+        const long long k0 = q / p.kept[1];
+        Val* o = reinterpret_cast<Val*>(p.out + k0 * p.out_k[0] + k1 * p.out_k[1] + k2 * p.out_k[2]);
+        *o     = R::finish(R::fold(R::lift(*o), t));
+      }
+    }
+    parity ^= 1;
+  }
+}
+
+template <class R>
+int launch_axis_row_tma(const AxisPlan& p, int sms, cudaStream_t stream)
+{
+  auto kernel            = axis_row_tma_kernel<R>;
+  static const int ready = [&] {
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ROWT_SMEM),
+                      "axis_row_tma_kernel smem opt-in");
+  }();
+  if (ready != CNB_OK) return ready;
+  const long long g = std::min<long long>(p.ncols, (long long)sms * ROWT_CTAS_PER_SM);
+  kernel<<<(unsigned)g, ROWT_THREADS, ROWT_SMEM, stream>>>(p, R(nullptr));
+  return check_cuda(cudaGetLastError(), "axis_row_tma_kernel launch");
+}
+
 template <int OP>
 int axis_red_by_type(int axis, const cnb_store_t* out, const cnb_store_t* in,
                      const cnb_store_t* where, long long axis_origin, cudaStream_t stream)
@@ -531,6 +694,16 @@ int axis_red_by_type(int axis, const cnb_store_t* out, const cnb_store_t* in,
       } else {
         p.vec = (p.in_a == isz) ? 1 : 0;
         LaunchScope scope(stream, KERNEL_AXIS_ROW, p.ncols * p.alen, algo_bytes);
+        static const bool use_tma = [] {
+          const char* e = getenv("CNB_AXIS_ROW_TMA");
+          return e == nullptr || atoi(e) != 0;
+        }();
+        const bool tma_ok = use_tma && sizeof(T) <= 16 && p.vec && where == nullptr &&
+                            reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && p.in_k[0] % 16 == 0 &&
+                            p.in_k[1] % 16 == 0 && p.in_k[2] % 16 == 0 &&
+                            (p.alen * isz) % 16 == 0 && p.alen * isz >= ROWT_CHUNK &&
+                            p.ncols >= sms / 2;
+        if (tma_ok) return launch_axis_row_tma<R>(p, sms, stream);
         if (p.alen >= 2048) {
           auto kernel = axis_row_kernel<R, RED_THREADS>;
           long long g = std::min<long long>(p.ncols, (long long)sms * 8);

@@ -150,6 +150,62 @@ def test_axis_reduction_all_pairs(op, dt):
         check_reduction(op, a, got, exp, shape[axis], f"axis {op}/{dt.name} {shape}@{axis}")
 
 
+# Long contiguous rows take the bulk-copy (TMA) pipeline of axis_red.inl when the row is >= 16 KB,
+# 16-byte aligned and there are >= SMs/2 rows; the shapes below hit full chunks, ragged last
+# chunks, several chunks per row, more rows than CTAs, and 3-D kept dims.
+LONG_ROWS = [((80, 4096), 1, np.float32), ((150, 5004), 1, np.float32), ((333, 16388), 1, np.float32),
+             ((76, 2048 + 6), 1, np.float64), ((90, 8192 + 8), 1, np.float16), ((100, 20000), 1, np.int8),
+             ((80, 1030), 1, np.complex128), ((75, 33000), 1, np.uint8), ((5, 20, 6000), 2, np.int32),
+             ((160, 4100), 1, np.int64), ((200, 16384 + 16), 1, np.bool_), ((600, 4096), 1, np.bool_)]
+
+
+@pytest.mark.parametrize("op", ["SUM", "MAX", "MIN", "ARGMAX", "ARGMIN", "PROD", "ALL", "ANY",
+                                "COUNT_NONZERO", "NANSUM", "NANARGMAX", "SUM_SQUARES"])
+@pytest.mark.parametrize("shape,axis,dt", LONG_ROWS,
+                         ids=lambda v: np.dtype(v).name if isinstance(v, type) else str(v))
+def test_axis_reduction_long_rows(op, shape, axis, dt):
+    dt = np.dtype(dt)
+    try:
+        ref.red_identity(op, dt)
+    except ref.InvalidOp:
+        pytest.skip("invalid")
+    rng = pu.rng_for("ared-long", op, dt.name, shape, axis)
+    a = red_input(op, dt, shape, rng)
+    if op in ("ARGMAX", "ARGMIN", "NANARGMAX") and dt.kind in "biu":
+        # many ties: the first occurrence must win across threads, warps and chunks
+        a = (a.astype(np.int64) % 3).astype(dt)
+    exp = ref.unary_red(op, a, axis, initial=python_prefill(op, dt))
+    got = thunk_reduce(op, a, axis=axis)
+    check_reduction(op, a, got, exp, shape[axis], f"long rows {op}/{dt.name} {shape}@{axis}")
+
+
+def test_axis_reduction_long_rows_views():
+    """pitched rows (16-byte aligned -> bulk-copy path), misaligned rows (-> LDG fallback), and the
+    extreme at the start / end of a row and on chunk boundaries"""
+    import cunumeric_b200 as cn
+
+    rng = pu.rng_for("ared-long-views")
+    a = rng.normal(size=(96, 3 * 4096 + 40)).astype(np.float32)
+    A = cn.array(a)
+    for sl in (np.s_[:, 8:8 + 8192], np.s_[:, 4:4 + 8192], np.s_[3:83, 16:], np.s_[:, :4096],
+               np.s_[::2, 12:12 + 4100]):
+        v, V = a[sl], A[sl]
+        assert np.array_equal(V.max(axis=1).__array__(), v.max(axis=1)), sl
+        assert np.array_equal(V.argmin(axis=1).__array__(), v.argmin(axis=1)), sl
+        got = V.sum(axis=1).__array__()
+        exp = ref.unary_red("SUM", np.ascontiguousarray(v), 1, initial=np.float32(0))
+        assert np.allclose(got, exp, rtol=0, atol=v.shape[1] * np.finfo(np.float32).eps *
+                           np.abs(v).sum(axis=1).max()), sl
+    b = np.zeros((80, 12288), dtype=np.float32)
+    for pos in (0, 1, 1023, 1024, 4095, 4096, 4097, 8191, 8192, 12287):
+        b[:] = 0
+        b[np.arange(80), pos] = 5.0
+        b[np.arange(80), min(pos + 4096, 12287)] = 5.0  # a later tie must lose
+        assert np.array_equal(cn.array(b).argmax(axis=1).__array__(), np.full(80, pos)), pos
+    # pre-filled output is folded in, not overwritten (reduce-accessor semantics)
+    assert np.array_equal(cn.array(b).max(axis=1, initial=7.0).__array__(), np.full(80, 7.0, np.float32))
+
+
 def test_reductions_on_views_and_where():
     import cunumeric_b200 as cn
 

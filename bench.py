@@ -44,6 +44,9 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=10_000_000,
                    help="options in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--fusion", choices=["on", "off"], default="on",
+                   help="on: elementwise chains run as fused kernels (default product path); "
+                        "off: one kernel per task")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
 
@@ -293,7 +296,8 @@ def trace_summary(cn, n_records: int, peak_gbs: float):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": None,
-        "kernel": f"ew_kernel<{names.get(top_key[0], top_key[0])}:{opname}:dtype{top_key[2]}>",
+        "kernel": (f"fused_kernel<{top_key[1]} elementwise tasks>" if top_key[0] == 1000 else
+                   f"ew_kernel<{names.get(top_key[0], top_key[0])}:{opname}:dtype{top_key[2]}>"),
         "launches": top["launches"],
         "avg_launch_ms": top["ms"] / top["launches"],
         "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
@@ -305,6 +309,8 @@ def trace_summary(cn, n_records: int, peak_gbs: float):
             nm = BinaryOpCode(key[1]).name
         elif key[0] == 43:
             nm = UnaryOpCode(key[1]).name
+        if key[0] == 1000:
+            return f"FUSED:{key[1]} tasks"
         return f"{names.get(key[0], key[0])}:{nm}:dtype{key[2]}"
 
     roofline["per_kernel"] = {
@@ -336,40 +342,68 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
     S, X, T = cn.array(Sh), cn.array(Xh), cn.array(Th)
     cn.synchronize()
 
-    sampler = ClockSampler(cn.runtime.device)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        call, put = black_scholes(S, X, T, R, V)
-    cn.synchronize()
-
-    # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides
-    ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
-    _lib.check(lib.cnb_trace_start(args.steps * (BLACK_SCHOLES_TASKS + 8)))
-    barrier(dist)
-    cn.synchronize()
-    sampler.mark_begin()
-    launches0 = cn.runtime.launch_count()
-    lib.cnb_event_record(ev0, cn.runtime.stream)
-    for _ in range(args.steps):
-        call, put = black_scholes(S, X, T, R, V)
-    lib.cnb_event_record(ev1, cn.runtime.stream)
-    cn.synchronize()
-    sampler.mark_end()
-    barrier(dist)
-    launches = cn.runtime.launch_count() - launches0
-    n_rec = lib.cnb_trace_stop()
+    from cunumeric_b200 import fusion
     import ctypes
 
-    ms = ctypes.c_float()
-    _lib.check(lib.cnb_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+    sampler = ClockSampler(cn.runtime.device)
+    sampler.start()
+
+    def timed(fused: bool, steps: int, sample_clocks: bool):
+        """W warm-up steps, then `steps` timed steps: CUDA events on the launching stream, barrier +
+        synchronize on both sides.  Every step ends with cn.flush(), so the step's results (call,
+        put) are materialised in HBM inside the timed region — nothing is left pending."""
+        fusion.set_mode("1" if fused else "0")
+        for _ in range(max(args.warmup, 3)):
+            call, put = black_scholes(S, X, T, R, V)
+            cn.flush()
+        cn.synchronize()
+        ev0, ev1 = lib.cnb_event_create(), lib.cnb_event_create()
+        _lib.check(lib.cnb_trace_start(steps * (BLACK_SCHOLES_TASKS + 8)))
+        barrier(dist)
+        cn.synchronize()
+        if sample_clocks:
+            sampler.mark_begin()
+        launches0 = cn.runtime.launch_count()
+        lib.cnb_event_record(ev0, cn.runtime.stream)
+        for _ in range(steps):
+            call, put = black_scholes(S, X, T, R, V)
+            cn.flush()
+        lib.cnb_event_record(ev1, cn.runtime.stream)
+        cn.synchronize()
+        if sample_clocks:
+            sampler.mark_end()
+        barrier(dist)
+        launches = cn.runtime.launch_count() - launches0
+        n_rec = lib.cnb_trace_stop()
+        ms = ctypes.c_float()
+        _lib.check(lib.cnb_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+        elapsed = max_over_ranks(dist, ms.value * 1e-3)
+        roofline, whole = trace_summary(cn, n_rec, peak_gbs)
+        if roofline is not None:
+            roofline["peak_source"] = peak_src
+            roofline.update(whole)
+            roofline["traffic"], roofline["traffic_source"] = load_traffic(roofline["kernel"])
+        return elapsed, launches, roofline
+
+    fused_on = args.fusion == "on" and fusion.enabled()
+    # the op-by-op leg (one kernel per task, as the reference issues them) is always measured too
+    obo_steps = args.steps if not fused_on else max(3, min(args.steps, 5))
+    obo_elapsed, obo_launches, obo_roofline = timed(False, obo_steps, not fused_on)
+    op_by_op = {"value": n * world * obo_steps / obo_elapsed, "unit": UNIT, "steps": obo_steps,
+                "ms_per_step": 1e3 * obo_elapsed / obo_steps, "gpu_launches": int(obo_launches),
+                "algorithmic_bytes_per_option": BLACK_SCHOLES_BYTES_PER_OPTION_F32,
+                "whole_step_algorithmic_gbs":
+                    BLACK_SCHOLES_BYTES_PER_OPTION_F32 * n * obo_steps / obo_elapsed / 1e9,
+                "roofline": obo_roofline}
+    if fused_on:
+        elapsed, launches, roofline = timed(True, args.steps, True)
+        bytes_per_option = 20  # 3 fp32 inputs + 2 fp32 outputs; 61 intermediates stay in registers
+    else:
+        elapsed, launches, roofline = obo_elapsed, obo_launches, obo_roofline
+        bytes_per_option = BLACK_SCHOLES_BYTES_PER_OPTION_F32
+    fusion.set_mode("1" if fused_on else "0")
     clocks = sampler.stop()
-    elapsed = max_over_ranks(dist, ms.value * 1e-3)
     value = n * world * args.steps / elapsed
-    roofline, whole = trace_summary(cn, n_rec, peak_gbs)
-    if roofline is not None:
-        roofline["peak_source"] = peak_src
-        roofline.update(whole)
-        roofline["traffic"], roofline["traffic_source"] = load_traffic(roofline["kernel"])
 
     # ---- e2e: the same step through the public API from HOST buffers (pinned), copies inside
     e2e = None
@@ -416,15 +450,20 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
             "data": "synthetic",
             "config": {"workload": "black_scholes fp32 1e8 options per GPU "
                                    "(examples/black_scholes.py, BASELINE.json configs[1]), "
-                                   "63 elementwise tasks per step issued op-by-op",
+                                   "63 elementwise tasks per step through the NumPy API; " +
+                                   ("the thunk layer captures the chain and runs it as ONE fused "
+                                    "kernel (bit-identical to op-by-op; `op_by_op` holds the "
+                                    "one-kernel-per-task measurement)" if fused_on else
+                                    "issued op-by-op, one kernel per task"),
+                       "execution": "fused" if fused_on else "op-by-op",
                        "options_per_gpu": n, "tasks_per_step": BLACK_SCHOLES_TASKS,
-                       "algorithmic_bytes_per_option": BLACK_SCHOLES_BYTES_PER_OPTION_F32,
-                       "l2_policy": "inputs and every temporary are 400 MB, larger than the "
-                                    "126 MB L2; no flush needed",
+                       "algorithmic_bytes_per_option": bytes_per_option,
+                       "l2_policy": "inputs, outputs (and op-by-op temporaries) are 400 MB each, "
+                                    "larger than the 126 MB L2; no flush needed",
                        "whole_step_algorithmic_gbs":
-                           BLACK_SCHOLES_BYTES_PER_OPTION_F32 * n * args.steps / elapsed / 1e9},
+                           bytes_per_option * n * args.steps / elapsed / 1e9},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e,
+            "op_by_op": op_by_op, "cpu_baseline": cpu, "e2e": e2e,
         }))
 
 

@@ -10,7 +10,11 @@ cn.runtime.ensure_initialized()
 lib = cn.runtime.lib
 e0, e1 = lib.cnb_event_create(), lib.cnb_event_create()
 
-def timeit(fn, reps=10):
+def timeit(fn0, reps=10):
+    def fn():
+        fn0()
+        cn.flush()
+
     for _ in range(3): fn()
     cn.synchronize()
     lib.cnb_event_record(e0, cn.runtime.stream)

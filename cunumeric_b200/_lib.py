@@ -85,6 +85,10 @@ PROTOTYPES = {
     "cnb_trace_start": (_i32, [_i32]),
     "cnb_trace_stop": (_i32, []),
     "cnb_trace_get": (_i32, [_i32, ctypes.POINTER(cnb_trace_record_t)]),
+    "cnb_module_load": (_i32, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    "cnb_module_get_kernel": (_i32, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "cnb_launch_fused": (_i32, [_vp, _vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64,
+                                ctypes.c_int64, _i32, _vp]),
     "cnb_last_error": (ctypes.c_char_p, []),
     "cnb_version": (ctypes.c_char_p, []),
     "cnb_comm_unique_id": (_i32, [_vp]),

@@ -11,6 +11,24 @@ from typing import Any, Dict, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from ..config import BinaryOpCode, UnaryOpCode, UnaryRedCode
+from ..deferred import DeferredArray
+from ..runtime import runtime as _runtime
+from ..store import Store
+
+
+def _single_gpu() -> bool:
+    return _runtime.world_size == 1
+
+
+_ndarray_cls: list = []
+
+
+def _ndarray_type():
+    if not _ndarray_cls:
+        from ..array import ndarray
+
+        _ndarray_cls.append(ndarray)
+    return _ndarray_cls[0]
 
 float_dtypes = ["e", "f", "d"]
 complex_dtypes = ["F", "D"]
@@ -243,6 +261,7 @@ class binary_ufunc(ufunc):
         self._nin, self._nout = len(in_ty), len(out_ty)
         self._op_code = op_code
         self._resolution_cache: Dict[Tuple[str, ...], Tuple[str, ...]] = {}
+        self._fast_types = {}
         self._red_code = red_code
         self._use_common_type = use_common_type
 
@@ -296,8 +315,80 @@ class binary_ufunc(ufunc):
         arrs = [a._astype(np.dtype(t), temporary=True) for a, t in zip(arrs, chosen)]
         return arrs, np.dtype(self._types[chosen])
 
+    # ---- fast path -----------------------------------------------------------------------------
+    # `array (op) array` with equal dtype and shape, and `floating array (op) Python float/int`
+    # (a weak scalar adopts the array's dtype) resolve to the same result as the general path
+    # below, without its per-call type arithmetic.  With fused chains the GPU work of a whole
+    # Black-Scholes step is ~0.6 ms, so the host cost per NumPy call is what bounds throughput.
+    _scalar_cache: Dict[Tuple[str, type, Any], Any] = {}
+    _fast_types: Dict[str, np.dtype]
+
+    @classmethod
+    def _weak_scalar(cls, value, dtype):
+        from ..array import ndarray
+        from ..deferred import DeferredArray
+        from ..store import Store
+
+        key = (dtype.char, type(value), value)
+        hit = cls._scalar_cache.get(key)
+        if hit is None:
+            if len(cls._scalar_cache) > 512:
+                cls._scalar_cache.clear()
+            with np.errstate(all="ignore"):
+                host = np.asarray(value).astype(dtype)
+            hit = ndarray(shape=(), dtype=dtype,
+                          thunk=DeferredArray(Store.from_scalar(host), host_scalar=host))
+            cls._scalar_cache[key] = hit
+        return hit
+
+    def _fast_call(self, a, b):
+        ndarray = _ndarray_type()
+        ta, tb = type(a), type(b)
+        if ta is ndarray and tb is ndarray:
+            dt = a.dtype
+            if dt != b.dtype or a.shape != b.shape or a.ndim == 0:
+                return NotImplemented
+            x1, x2, shape = a, b, a.shape
+        elif ta is ndarray and (tb is float or tb is int):
+            dt = a.dtype
+            if dt.kind != "f" or a.ndim == 0 or b != b:
+                return NotImplemented
+            x1, x2, shape = a, self._weak_scalar(b, dt), a.shape
+        elif tb is ndarray and (ta is float or ta is int):
+            dt = b.dtype
+            if dt.kind != "f" or b.ndim == 0 or a != a:
+                return NotImplemented
+            x1, x2, shape = self._weak_scalar(a, dt), b, b.shape
+        else:
+            return NotImplemented
+        res = self._fast_types.get(dt.char)
+        if res is None:
+            res = self._types.get((dt.char, dt.char))
+            if res is None:
+                return NotImplemented
+            res = self._fast_types[dt.char] = np.dtype(res)
+        t1, t2 = x1._thunk, x2._thunk
+        if type(t1) is DeferredArray and type(t2) is DeferredArray and _single_gpu():
+            # brand-new output: no aliasing to resolve, operands are same-shape or 0-d
+            out = DeferredArray(Store.empty(shape, res))
+            b1, b2 = t1.base, t2.base
+            if b1.shape != shape:
+                b1 = b1.broadcast_to(shape)
+            if b2.shape != shape:
+                b2 = b2.broadcast_to(shape)
+            out.binary_op_prepared(self._op_code, b1, b2)
+            return ndarray(shape, thunk=out)
+        result = ndarray(shape, res, inputs=(x1, x2))
+        result._thunk.binary_op(self._op_code, t1, t2, True, ())
+        return result
+
     def __call__(self, *args: Any, out=None, where: Any = True, casting: str = "same_kind",
                  order: str = "K", dtype=None, **kwargs: Any):
+        if out is None and where is True and dtype is None and len(args) == 2 and \
+                self._use_common_type and not kwargs:
+            fast = self._fast_call(args[0], args[1])
+            if fast is not NotImplemented:
+                return fast
         arrs, (out,), out_shape, where = self._prepare_operands(*args, out=out, where=where)
         orig_args = args[: self.nin]
         precision_fixed = False

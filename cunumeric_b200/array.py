@@ -288,20 +288,23 @@ class ndarray:
 
     # ------------------------------------------------------------------ operators -> ufuncs
     def _binop(name):  # noqa: N805
-        def fwd(self, rhs):
-            from . import _ufunc
+        cache = []
 
-            return getattr(_ufunc, name)(self, rhs)
+        def uf():
+            if not cache:
+                from . import _ufunc
+
+                cache.append(getattr(_ufunc, name))
+            return cache[0]
+
+        def fwd(self, rhs):
+            return uf()(self, rhs)
 
         def rev(self, lhs):
-            from . import _ufunc
-
-            return getattr(_ufunc, name)(lhs, self)
+            return uf()(lhs, self)
 
         def inplace(self, rhs):
-            from . import _ufunc
-
-            return getattr(_ufunc, name)(self, rhs, out=self)
+            return uf()(self, rhs, out=self)
 
         return fwd, rev, inplace
 

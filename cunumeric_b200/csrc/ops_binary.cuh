@@ -92,7 +92,7 @@ struct Divide {
   static constexpr bool valid = true;
   using Out  = std::conditional_t<std::is_integral<T>::value, double, T>;
   using Rhs2 = T;
-  __host__ Divide(const void*) {}
+  __host__ __device__ Divide(const void* = nullptr) {}
   __device__ __forceinline__ Out operator()(const T& a, const T& b) const
   {
     if constexpr (std::is_integral<T>::value)
@@ -400,7 +400,7 @@ struct Ldexp {
   static constexpr bool valid = is_float_v<T>;
   using Out  = T;
   using Rhs2 = int32_t;
-  __host__ Ldexp(const void*) {}
+  __host__ __device__ Ldexp(const void* = nullptr) {}
   __device__ __forceinline__ T operator()(const T& a, const int32_t& b) const
   {
     if constexpr (is_half_v<T>)
@@ -457,7 +457,7 @@ struct FloatPower {
     std::is_same<T, double>::value || std::is_same<T, c128>::value || std::is_same<T, c64>::value;
   using Out  = std::conditional_t<std::is_same<T, c64>::value, c128, T>;
   using Rhs2 = T;
-  __host__ FloatPower(const void*) {}
+  __host__ __device__ FloatPower(const void* = nullptr) {}
   __device__ __forceinline__ Out operator()(const T& a, const T& b) const
   {
     if constexpr (std::is_same<T, double>::value)

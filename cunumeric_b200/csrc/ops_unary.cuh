@@ -79,7 +79,7 @@ CNB_FC_UNOP(Log2, log2f(x), log2(x), cuda::std::log(x) / cuda::std::log(T(2)))
   struct NAME {                                                                         \
     static constexpr bool valid = true;                                                 \
     using Out = std::conditional_t<std::is_integral<T>::value, double, T>;              \
-    __host__ NAME(const void*) {}                                                       \
+    __host__ __device__ NAME(const void* = nullptr) {}                                                       \
     __device__ __forceinline__ Out operator()(const T& x_) const                        \
     {                                                                                   \
       if constexpr (is_half_v<T>) {                                                     \
@@ -165,7 +165,7 @@ struct Absolute {
     using type = V;
   };
   using Out = typename OutOf<T>::type;
-  __host__ Absolute(const void*) {}
+  __host__ __device__ Absolute(const void* = nullptr) {}
   __device__ __forceinline__ Out operator()(const T& x) const
   {
     if constexpr (is_complex_v<T>)
@@ -380,7 +380,7 @@ template <typename T>
 struct Real {
   static constexpr bool valid = is_complex_v<T>;
   using Out = typename Absolute<T>::Out;
-  __host__ Real(const void*) {}
+  __host__ __device__ Real(const void* = nullptr) {}
   __device__ __forceinline__ Out operator()(const T& x) const
   {
     if constexpr (is_complex_v<T>)
@@ -393,7 +393,7 @@ template <typename T>
 struct Imag {
   static constexpr bool valid = is_complex_v<T>;
   using Out = typename Absolute<T>::Out;
-  __host__ Imag(const void*) {}
+  __host__ __device__ Imag(const void* = nullptr) {}
   __device__ __forceinline__ Out operator()(const T& x) const
   {
     if constexpr (is_complex_v<T>)

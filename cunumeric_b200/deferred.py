@@ -12,7 +12,7 @@ from typing import Any, Optional, Sequence
 
 import numpy as np
 
-from . import _lib
+from . import _lib, fusion
 from .config import BinaryOpCode, ConvertCode, UnaryOpCode, UnaryRedCode, MAX_DIM
 from .runtime import runtime
 from .store import Store
@@ -95,6 +95,26 @@ class HostFuture:
             self.wait()
         except Exception:
             pass
+
+
+def launch_elementwise(kind: str, op: int, nan_op: int, lhs: Store, ins: Sequence[Store]) -> None:
+    """One elementwise task through the per-task C ABI (fusion.py replays chains with this)."""
+    lib = runtime.lib
+    d_out = lhs.descriptor()
+    d_in = [s.descriptor() for s in ins]
+    if kind == "U":
+        rc = lib.cnb_unary_op(op, ctypes.byref(d_out), None, ctypes.byref(d_in[0]), None, runtime.stream)
+    elif kind == "B":
+        rc = lib.cnb_binary_op(op, ctypes.byref(d_out), ctypes.byref(d_in[0]), ctypes.byref(d_in[1]),
+                               None, runtime.stream)
+    elif kind == "W":
+        rc = lib.cnb_where(ctypes.byref(d_out), ctypes.byref(d_in[0]), ctypes.byref(d_in[1]),
+                           ctypes.byref(d_in[2]), runtime.stream)
+    elif kind == "C":
+        rc = lib.cnb_convert(nan_op, ctypes.byref(d_out), ctypes.byref(d_in[0]), runtime.stream)
+    else:
+        raise ValueError(kind)
+    _lib.check(rc)
 
 
 def _rep(thunk):
@@ -219,7 +239,8 @@ class DeferredArray:
         return copy
 
     def _broadcast(self, shape) -> Store:
-        return self.base.broadcast_to(shape)
+        base = self.base
+        return base if base.shape == shape else base.broadcast_to(shape)
 
     # ------------------------------------------------------------------ UNARY_OP
     def unary_op(self, op: UnaryOpCode, src: "DeferredArray", where: Any = True,
@@ -234,6 +255,8 @@ class DeferredArray:
                 src = extra_out._copy_if_overlapping(src)
             out2 = multiout[0].base.descriptor()
         extra = _host_scalars(args, src.dtype) if op == UnaryOpCode.CLIP else None
+        if out2 is None and extra is None and fusion.capture("U", int(op), lhs, (rhs,)):
+            return
         d_out, d_in = lhs.descriptor(), rhs.descriptor()
         _lib.check(runtime.lib.cnb_unary_op(int(op), ctypes.byref(d_out),
                                             None if out2 is None else ctypes.byref(out2),
@@ -248,9 +271,21 @@ class DeferredArray:
         rhs1 = src1._broadcast(lhs.shape)
         rhs2 = src2._broadcast(lhs.shape)
         extra = _host_scalars(args, np.float64) if op_code == BinaryOpCode.ISCLOSE else None
+        if extra is None and fusion.capture("B", int(op_code), lhs, (rhs1, rhs2)):
+            return
         d_out, d1, d2 = lhs.descriptor(), rhs1.descriptor(), rhs2.descriptor()
         _lib.check(runtime.lib.cnb_binary_op(int(op_code), ctypes.byref(d_out), ctypes.byref(d1),
                                              ctypes.byref(d2), _vp(extra), runtime.stream))
+
+    def binary_op_prepared(self, op_code: int, rhs1: Store, rhs2: Store) -> None:
+        """binary_op for a freshly allocated output and operands already broadcast to its shape
+        (the ufunc fast path): nothing to replicate, no aliasing to resolve, no extra scalars."""
+        lhs = self.base
+        if fusion.capture("B", int(op_code), lhs, (rhs1, rhs2)):
+            return
+        d_out, d1, d2 = lhs.descriptor(), rhs1.descriptor(), rhs2.descriptor()
+        _lib.check(runtime.lib.cnb_binary_op(int(op_code), ctypes.byref(d_out), ctypes.byref(d1),
+                                             ctypes.byref(d2), None, runtime.stream))
 
     def isclose(self, rhs1, rhs2, rtol: float, atol: float, equal_nan: bool) -> None:
         assert not equal_nan
@@ -286,6 +321,8 @@ class DeferredArray:
         m = self._copy_if_overlapping(_rep(mask))._broadcast(lhs.shape)
         a = self._copy_if_overlapping(_rep(one))._broadcast(lhs.shape)
         b = self._copy_if_overlapping(_rep(two))._broadcast(lhs.shape)
+        if fusion.capture("W", 0, lhs, (m, a, b)):
+            return
         d_out, dm, da, db = lhs.descriptor(), m.descriptor(), a.descriptor(), b.descriptor()
         _lib.check(runtime.lib.cnb_where(ctypes.byref(d_out), ctypes.byref(dm), ctypes.byref(da),
                                          ctypes.byref(db), runtime.stream))
@@ -300,6 +337,8 @@ class DeferredArray:
             return
         rhs = self._copy_if_overlapping(rhs)
         src = rhs._broadcast(lhs.shape)
+        if fusion.capture("C", 0, lhs, (src,), int(nan_op)):
+            return
         d_out, d_in = lhs.descriptor(), src.descriptor()
         _lib.check(runtime.lib.cnb_convert(int(nan_op), ctypes.byref(d_out), ctypes.byref(d_in),
                                            runtime.stream))

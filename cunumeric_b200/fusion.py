@@ -1,0 +1,689 @@
+"""Lazy fusion of elementwise task chains.
+
+The reference issues one task per NumPy operation (deferred.py:3139 `unary_op`, :3302 `binary_op`,
+:3366 `where`, :1348 `convert`), so Black-Scholes moves 604 B per option and the stencil 128 B per
+point although 20 B / ~40 B would do.  Here the thunk layer *captures* elementwise tasks instead of
+launching them; a run of tasks over one iteration space becomes ONE generated kernel in which
+every intermediate lives in registers and only the outputs somebody can still observe are stored.
+
+Semantics are exactly those of eager, in-order execution:
+* a captured chain is flushed before anything else can touch device memory — every consumer
+  obtains pointers through `Store.ptr`, which flushes first (other tasks, reductions, copies to
+  and from the host, NCCL, synchronize);
+* a task joins the open chain only if it has the same shape and is free of cross-element hazards
+  with it: an operand that overlaps something the chain writes must be the *same window* (then the
+  value is taken from registers, element for element); otherwise the chain is flushed first;
+* an output is dropped only if no `Store` window onto its buffer is alive any more (a Python
+  temporary that was freed) — nobody could read it;
+* the generated kernel composes the very same device functors as the per-task kernels
+  (ops_binary.cuh / ops_unary.cuh / ops_convert.cuh, compiled with the same flags, -fmad=false), so
+  every intermediate is rounded exactly as if it had been stored and re-loaded: results are
+  bit-identical to op-by-op execution (tests/test_fusion.py).
+
+Kernels are compiled with nvcc for sm_100a the second time a chain signature is seen (the first
+time the chain simply runs op-by-op) and cached in memory and on disk
+(cunumeric_b200/_fused_cache/); `__graft_entry__.build()` pre-compiles the chains of the benchmark
+programs by tracing them without a device.  A chain whose kernel is not (yet) available, or whose
+layout the generated kernel does not cover, is replayed op-by-op through the C ABI — always valid.
+
+CUNUMERIC_B200_FUSION = 0 (off) | 1 (default) | always (compile on first sight).
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import shutil
+import subprocess
+import tempfile
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .config import MAX_DIM, dtype_code
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CACHE_DIR = os.environ.get("CUNUMERIC_B200_FUSED_CACHE", os.path.join(_HERE, "_fused_cache"))
+_CSRC = os.path.join(_HERE, "csrc")
+_INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+MAX_TASKS = 192
+MAX_INPUTS = 24
+MAX_OUTPUTS = 8
+THREADS = 256
+
+_mode = os.environ.get("CUNUMERIC_B200_FUSION", "1").lower()
+
+
+def set_mode(mode: str) -> str:
+    """'0' off, '1' compile a chain the second time it is seen, 'always' compile at first sight."""
+    global _mode
+    flush()
+    old, _mode = _mode, str(mode).lower()
+    return old
+
+
+def enabled() -> bool:
+    return _mode not in ("0", "off", "false")
+
+
+class _Window:
+    """A (buffer, offset, shape, strides, dtype) window, held without a Store so that it does not
+    count as a user of the buffer."""
+
+    __slots__ = ("buffer", "offset", "shape", "strides", "dtype", "key", "lo", "hi")
+
+    def __init__(self, store) -> None:
+        self.buffer = store.buffer
+        self.offset = store.offset
+        self.shape = store.shape
+        self.strides = store.strides
+        self.dtype = store.dtype
+        self.key = (id(store.buffer), store.offset, store.shape, store.strides, store.dtype.num)
+        lo = hi = store.offset
+        for n, s in zip(store.shape, store.strides):
+            if s >= 0:
+                hi += (n - 1) * s
+            else:
+                lo += (n - 1) * s
+        self.lo, self.hi = lo, hi + store.dtype.itemsize
+
+    def overlaps(self, other: "_Window") -> bool:
+        return self.buffer is other.buffer and self.lo < other.hi and other.lo < self.hi
+
+    def store(self):
+        from .store import Store
+
+        return Store(self.buffer, self.dtype, self.shape, self.strides, self.offset)
+
+
+class _Task:
+    __slots__ = ("kind", "op", "nan_op", "ins", "out", "window")
+
+    def __init__(self, kind, op, nan_op, ins, out, window) -> None:
+        self.kind, self.op, self.nan_op, self.ins, self.out, self.window = (
+            kind, op, nan_op, ins, out, window)
+
+
+class _Chain:
+    def __init__(self) -> None:
+        self.shape: Optional[Tuple[int, ...]] = None
+        self.tasks: List[_Task] = []
+        self.dtypes: List[np.dtype] = []      # per value id
+        self.ext: List[Optional[_Window]] = []  # per value id: the window of an external input
+        self.ext_index: dict = {}             # key -> value id
+        self.written: dict = {}               # key -> (value id, window), latest write
+        # hazard index: id(buffer) -> windows written / read through, so that an overlap test only
+        # looks at windows of the same allocation (usually none)
+        self.w_by_buf: dict = {}
+        self.r_by_buf: dict = {}
+
+
+_PLAIN_DTYPES = frozenset(np.dtype(t) for t in (
+    np.bool_, np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64,
+    np.float16, np.float32, np.float64, np.complex64, np.complex128))
+_chain = _Chain()
+_flushing = False
+_seen: dict = {}
+_kernels: dict = {}   # signature hash -> (vec kernel, strided kernel, plan class) | None (= unusable)
+stats = {"captured": 0, "fused_launches": 0, "fused_tasks": 0, "replayed_tasks": 0,
+         "elided_tasks": 0, "compiled": 0}
+
+
+_rt: list = []
+
+
+def _get_runtime():
+    from .runtime import runtime
+
+    _rt.append(runtime)
+    return runtime
+
+
+def pending() -> bool:
+    return bool(_chain.tasks) and not _flushing
+
+
+# ---------------------------------------------------------------------------------------------
+# capture
+# ---------------------------------------------------------------------------------------------
+def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> bool:
+    """Try to defer an elementwise task `lhs = kind/op(rhs...)` (stores already broadcast to
+    lhs.shape).  Returns False if the caller must launch it eagerly."""
+    global _chain
+    if _flushing or _mode in ("0", "off", "false"):
+        return False
+    runtime = _rt[0] if _rt else _get_runtime()
+    if runtime.lib is None and not runtime.dry_run:
+        runtime.ensure_initialized()  # no device -> fail loudly right here
+    shape = lhs.shape
+    if len(shape) > MAX_DIM or lhs.size == 0:
+        return False
+    for n, st in zip(shape, lhs.strides):
+        if st == 0 and n > 1:
+            return False
+    if lhs.dtype not in _PLAIN_DTYPES:
+        return False
+    for r in rhs:
+        if r.shape != shape or r.dtype not in _PLAIN_DTYPES:
+            return False
+    c = _chain
+    if c.tasks and (c.shape != shape or len(c.tasks) >= MAX_TASKS or
+                    len(c.ext_index) + len(rhs) > MAX_INPUTS):
+        flush()
+        c = _chain
+    out_w = lhs._win
+    if out_w is None:
+        out_w = lhs._win = _Window(lhs)
+    in_w = []
+    for r in rhs:
+        w = r._win
+        if w is None:
+            w = r._win = _Window(r)
+        in_w.append(w)
+    if c.tasks:
+        hazard = False
+        written = c.written
+        for w in in_w:  # read of something the chain writes through a different window
+            if w.key not in written:
+                for ww in c.w_by_buf.get(id(w.buffer), ()):
+                    if w.lo < ww.hi and ww.lo < w.hi:
+                        hazard = True
+        if not hazard:
+            bid = id(out_w.buffer)
+            if out_w.key not in written:
+                for ww in c.w_by_buf.get(bid, ()):  # write over a chain output, different window
+                    if out_w.lo < ww.hi and ww.lo < out_w.hi:
+                        hazard = True
+            for rw in c.r_by_buf.get(bid, ()):  # write over something read through another window
+                if rw.key != out_w.key and out_w.lo < rw.hi and rw.lo < out_w.hi:
+                    hazard = True
+        if hazard:
+            flush()
+            c = _chain
+    c.shape = shape
+    ins = []
+    for w in in_w:
+        hit = c.written.get(w.key)
+        if hit is not None:
+            ins.append(hit[0])
+            continue
+        vid = c.ext_index.get(w.key)
+        if vid is None:
+            vid = len(c.dtypes)
+            c.dtypes.append(w.dtype)
+            c.ext.append(w)
+            c.ext_index[w.key] = vid
+            c.r_by_buf.setdefault(id(w.buffer), []).append(w)
+        ins.append(vid)
+    # an input window of THIS task that overlaps its own output through a different window is
+    # resolved by the caller (DeferredArray._copy_if_overlapping) before we get here
+    out = len(c.dtypes)
+    c.dtypes.append(out_w.dtype)
+    c.ext.append(None)
+    if out_w.key not in c.written:
+        c.w_by_buf.setdefault(id(out_w.buffer), []).append(out_w)
+    c.written[out_w.key] = (out, out_w)
+    c.tasks.append(_Task(kind, int(op), int(nan_op), tuple(ins), out, out_w))
+    stats["captured"] += 1
+    return True
+
+
+# ---------------------------------------------------------------------------------------------
+# flush
+# ---------------------------------------------------------------------------------------------
+def flush() -> None:
+    """Run the open chain (fused if possible, else op-by-op) and start a new one."""
+    global _chain, _flushing
+    if _flushing or not _chain.tasks:
+        return
+    c, _chain = _chain, _Chain()
+    _flushing = True
+    try:
+        _run_chain(c)
+    finally:
+        _flushing = False
+
+
+def _run_chain(c: _Chain) -> None:
+    from .runtime import runtime
+
+    # outputs somebody can still observe: latest write per window, buffer still has a live Store
+    live = [(vid, w) for vid, w in c.written.values() if w.buffer.users > 0]
+    needed = set(v for v, _ in live)
+    keep: List[_Task] = []
+    for t in reversed(c.tasks):
+        if t.out in needed:
+            keep.append(t)
+            needed.update(t.ins)
+    keep.reverse()
+    stats["elided_tasks"] += len(c.tasks) - len(keep)
+    if not keep:
+        return
+    if len(keep) == 1 or len(live) > MAX_OUTPUTS:
+        _replay(c, keep)
+        return
+    ext_ids = sorted(v for v in needed if c.ext[v] is not None)
+    # canonical numbering: external inputs in order of first use, then tasks in order
+    order: dict = {}
+    for t in keep:
+        for v in t.ins:
+            if c.ext[v] is not None and v not in order:
+                order[v] = len(order)
+    n_in = len(order)
+    for t in keep:
+        order[t.out] = len(order)
+    assert len(ext_ids) == n_in
+    # (dtype code, is-scalar): a stride-0 operand (Python scalar / 0-d array) is read once per
+    # thread and does not count towards the bytes in flight
+    in_codes = tuple((dtype_code(c.dtypes[v]), all(st == 0 for st in c.ext[v].strides))
+                     for v in order if c.ext[v] is not None)
+    tasks_sig = tuple((t.kind, t.op, t.nan_op, tuple(order[v] for v in t.ins), order[t.out],
+                       dtype_code(c.dtypes[t.out])) for t in keep)
+    outs = sorted(((order[v], dtype_code(w.dtype)) for v, w in live))
+    sig = (in_codes, tasks_sig, tuple(outs))
+    entry = _lookup(sig)
+    if entry is None:
+        _replay(c, keep)
+        return
+    # operands: stored outputs first (in signature order), then inputs (in signature order)
+    out_windows = [w for _, w in sorted(((order[v], w) for v, w in live), key=lambda p: p[0])]
+    in_windows = [c.ext[v] for v in order if c.ext[v] is not None]
+    if runtime.dry_run:
+        return
+    if not _launch(entry, c.shape, out_windows, in_windows, len(keep)):
+        _replay(c, keep)
+
+
+def _replay(c: _Chain, tasks: List[_Task]) -> None:
+    """Op-by-op execution of (the needed part of) a chain through the per-task C ABI."""
+    from .runtime import runtime
+
+    if runtime.dry_run:
+        return
+    from . import deferred
+
+    produced = {}
+    for t in tasks:
+        ins = []
+        for v in t.ins:
+            w = c.ext[v] if c.ext[v] is not None else produced[v]
+            ins.append(w.store())
+        deferred.launch_elementwise(t.kind, t.op, t.nan_op, t.window.store(), ins)
+        produced[t.out] = t.window
+    stats["replayed_tasks"] += len(tasks)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel lookup / generation / compilation
+# ---------------------------------------------------------------------------------------------
+def _hash(sig) -> str:
+    return hashlib.sha1(repr(sig).encode()).hexdigest()[:20]
+
+
+def _lookup(sig):
+    h = _hash(sig)
+    if h in _kernels:
+        return _kernels[h]
+    path = os.path.join(_CACHE_DIR, f"fused_{h}.cubin")
+    if not os.path.exists(path):
+        n = _seen.get(h, 0) + 1
+        _seen[h] = n
+        if _mode != "always" and n < 2:
+            return None  # first sighting: run op-by-op, compile when the chain comes back
+        if not _compile(sig, h, path):
+            _kernels[h] = None
+            return None
+    from .runtime import runtime
+
+    if runtime.dry_run:
+        return ("dry", h)
+    entry = _load(sig, h, path)
+    _kernels[h] = entry
+    return entry
+
+
+def _nvcc() -> Optional[str]:
+    exe = shutil.which("nvcc")
+    if exe is None and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        exe = "/usr/local/cuda/bin/nvcc"
+    return exe
+
+
+def _compile(sig, h: str, path: str) -> bool:
+    exe = _nvcc()
+    if exe is None:
+        return False
+    os.makedirs(_CACHE_DIR, exist_ok=True)
+    src = generate_source(sig, h)
+    src_path = os.path.join(_CACHE_DIR, f"fused_{h}.cu")
+    with open(src_path, "w") as f:
+        f.write(src)
+    fd, tmp = tempfile.mkstemp(suffix=".cubin", dir=_CACHE_DIR)
+    os.close(fd)
+    cmd = [exe, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+           "-fmad=false", "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177",
+           "-I", _CSRC, "-I", _INCLUDE, "-cubin", "-o", tmp, src_path]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        os.unlink(tmp)
+        with open(os.path.join(_CACHE_DIR, f"fused_{h}.err"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return False
+    os.replace(tmp, path)  # atomic: ranks of one job may compile the same chain concurrently
+    stats["compiled"] += 1
+    return True
+
+
+def _plan_type(nops: int):
+    class Operand(ctypes.Structure):
+        _fields_ = [("ptr", ctypes.c_void_p), ("inner_stride", ctypes.c_int64),
+                    ("row_stride", ctypes.c_int64)]
+
+    class Plan(ctypes.Structure):
+        _fields_ = [("inner", ctypes.c_int64), ("rows", ctypes.c_int64),
+                    ("tiles_per_row", ctypes.c_int64), ("num_tiles", ctypes.c_int64),
+                    ("vec", ctypes.c_int32), ("out_pad", ctypes.c_int32),
+                    ("op", Operand * nops)]
+
+    return Plan
+
+
+def _load(sig, h: str, path: str):
+    from .runtime import runtime
+
+    runtime.ensure_initialized()
+    with open(path, "rb") as f:
+        image = f.read()
+    module = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(image, len(image))
+    if runtime.lib.cnb_module_load(buf, len(image), ctypes.byref(module)) != 0:
+        return None
+    kernels = []
+    for suffix in ("vec", "str"):
+        k = ctypes.c_void_p()
+        if runtime.lib.cnb_module_get_kernel(module, f"fused_{h}_{suffix}".encode(),
+                                             ctypes.byref(k)) != 0:
+            return None
+        kernels.append(k)
+    in_codes, tasks_sig, outs = sig
+    geo = _geometry(sig)
+    return (kernels[0], kernels[1], _plan_type(len(outs) + len(in_codes)), geo, buf)
+
+
+_SIZES = [1, 1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 8, 16]  # bytes per dtype code (bool ... complex128)
+
+
+def _geometry(sig):
+    """Elements per 128-bit chunk (E), chunks in flight per thread (U) and tile size — the rules of
+    cnb_elementwise.cuh:EwShape applied to the operands the fused kernel actually loads / stores."""
+    in_codes, tasks_sig, outs = sig
+    in_sizes = [_SIZES[c] for c, _ in in_codes]
+    arr_sizes = [_SIZES[c] for c, scalar in in_codes if not scalar]
+    out_sizes = [_SIZES[c] for _, c in outs]
+    max_out = max(out_sizes)
+    max_in = max(arr_sizes) if arr_sizes else 1
+    e = max(1, min(16 // max_out, 64 // max_in))
+    in_bytes = sum(arr_sizes)
+    u = max(1, min(8, 128 // max(1, e * in_bytes))) if in_bytes else 4
+    if len(tasks_sig) > 16:
+        u = min(u, 2)
+    # strided kernel: batches of B elements per thread.  Operands of a fused chain are often shifted
+    # views of one array (the stencil's five neighbours), whose loads mostly hit L1/L2 but still
+    # occupy the thread's load slots, so keep >= 4 elements (~160 B of requests) in flight
+    b = max(4, min(16, 64 // max(1, in_bytes)))
+    while e * u < b:
+        u += 1
+    return {"E": e, "U": u, "B": b, "TILE": THREADS * e * u, "in_sizes": in_sizes,
+            "out_sizes": out_sizes}
+
+
+def generate_source(sig, h: str) -> str:
+    in_codes, tasks_sig, outs = sig
+    geo = _geometry(sig)
+    n_in, n_out = len(in_codes), len(outs)
+    nops = n_in + n_out
+    E, U, B = geo["E"], geo["U"], geo["B"]
+    L: List[str] = []
+    L.append(f"// generated by cunumeric_b200/fusion.py — fused chain {h}: {len(tasks_sig)} tasks, "
+             f"{n_in} inputs, {n_out} stored outputs")
+    L.append('#include "cnb_elementwise.cuh"\n#include "ops_binary.cuh"\n#include "ops_unary.cuh"\n'
+             '#include "ops_convert.cuh"\nusing namespace cnb;\nnamespace {')
+    L.append(f"constexpr int NOPS = {nops}, E = {E}, U = {U}, B = {B}, TILE = {THREADS} * E * U;")
+    L.append("struct FOperand { char* ptr; long long inner_stride; long long row_stride; };")
+    L.append("struct FPlan { long long inner, rows, tiles_per_row, num_tiles; int vec, out_pad; "
+             "FOperand op[NOPS]; };")
+    L.append("""template <typename T, int N>
+__device__ __forceinline__ void fload_vec(Pack<T, N>& r, const FOperand& o, long long off, long long e)
+{
+  if (o.inner_stride == 0) {
+    Pack<T, 1> s;
+    ld_bytes<sizeof(T)>(s.raw, o.ptr + off);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = s[0];
+  } else {
+    ld_bytes<sizeof(T) * N>(r.raw, o.ptr + off + e * (long long)sizeof(T));
+  }
+}
+template <typename T>
+__device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long long off, long long e)
+{
+  ld_bytes<sizeof(T)>(r.raw, o.ptr + off + e * o.inner_stride);
+}""")
+    # value types
+    vtype = {}
+    scalar_in = [scalar for _, scalar in in_codes]
+    for i, (code, _) in enumerate(in_codes):
+        vtype[i] = code
+    for kind, op, nan_op, ins, out, code in tasks_sig:
+        vtype[out] = code
+    for v, code in sorted(vtype.items()):
+        L.append(f"using T{v} = type_of<{code}>;")
+    in_params = ", ".join(f"const T{i}& v{i}" for i in range(n_in))
+    out_params = ", ".join(f"T{v}& y{j}" for j, (v, _) in enumerate(outs))
+    L.append(f"__device__ __forceinline__ void body({in_params}{', ' if in_params else ''}{out_params})\n{{")
+    for kind, op, nan_op, ins, out, code in tasks_sig:
+        if kind == "B":
+            a, b = ins
+            L.append(f"  using F{out} = typename BinaryFn<{op}>::template fn<T{a}>;")
+            L.append(f"  static_assert(F{out}::valid && std::is_same<typename F{out}::Out, T{out}>::value && "
+                     f"std::is_same<typename F{out}::Rhs2, T{b}>::value, \"task {out}\");")
+            L.append(f"  const T{out} v{out} = F{out}()(v{a}, v{b});")
+        elif kind == "U":
+            (a,) = ins
+            L.append(f"  using F{out} = typename UnaryFn<{op}>::template fn<T{a}>;")
+            L.append(f"  static_assert(F{out}::valid && std::is_same<typename F{out}::Out, T{out}>::value, "
+                     f"\"task {out}\");")
+            L.append(f"  const T{out} v{out} = F{out}()(v{a});")
+        elif kind == "C":
+            (a,) = ins
+            L.append(f"  static_assert(ConvertFn<{nan_op}, T{out}, T{a}>::valid, \"task {out}\");")
+            L.append(f"  T{out} v{out};\n  {{ Unused u_; ConvertFn<{nan_op}, T{out}, T{a}>()(v{out}, u_, v{a}, u_, u_); }}")
+        elif kind == "W":
+            m, a, b = ins
+            L.append(f"  static_assert(std::is_same<T{m}, bool>::value && std::is_same<T{a}, T{out}>::value && "
+                     f"std::is_same<T{b}, T{out}>::value, \"task {out}\");")
+            L.append(f"  const T{out} v{out} = v{m} ? v{a} : v{b};")
+        else:
+            raise ValueError(kind)
+    for j, (v, _) in enumerate(outs):
+        L.append(f"  y{j} = v{v};")
+    L.append("}\n}  // namespace")
+
+    # operand k: outputs 0..n_out-1, inputs n_out..nops-1
+    def rowoffs():
+        return "\n".join(f"    const long long off{k} = row * plan.op[{k}].row_stride;" for k in range(nops))
+
+    hoist = "".join(f"  Pack<T{i}, 1> s{i};\n  ld_bytes<sizeof(T{i})>(s{i}.raw, plan.op[{n_out + i}].ptr);\n"
+                    for i in range(n_in) if scalar_in[i])
+    head = """  const int tid = threadIdx.x;
+""" + hoist + """  for (long long tile = blockIdx.x; tile < plan.num_tiles; tile += gridDim.x) {
+    long long row = 0, ct = tile;
+    if (plan.rows > 1) {
+      row = tile / plan.tiles_per_row;
+      ct  = tile - row * plan.tiles_per_row;
+    }
+    const long long col0 = ct * TILE;
+""" + rowoffs() + "\n"
+
+    def scalar_elem(ind: str, e: str) -> str:
+        s = []
+        for i in range(n_in):
+            if not scalar_in[i]:
+                s.append(f"{ind}Pack<T{i}, 1> a{i};\n{ind}fload_one<T{i}>(a{i}, plan.op[{n_out + i}], off{n_out + i}, {e});")
+        for j, (v, _) in enumerate(outs):
+            s.append(f"{ind}Pack<T{v}, 1> r{j};")
+        args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[0]" for i in range(n_in)] +
+                         [f"r{j}[0]" for j in range(n_out)])
+        s.append(f"{ind}body({args});")
+        for j, (v, _) in enumerate(outs):
+            s.append(f"{ind}st_bytes<sizeof(T{v})>(plan.op[{j}].ptr + off{j} + {e} * plan.op[{j}].inner_stride, r{j}.raw);")
+        return "\n".join(s)
+
+    # ---- vector kernel
+    L.append(f'extern "C" __global__ void __launch_bounds__({THREADS}) fused_{h}_vec(const __grid_constant__ FPlan plan)\n{{')
+    L.append(head)
+    L.append("    if (col0 + TILE > plan.inner) {\n      for (long long e = col0 + tid; e < plan.inner; e += %d) {" % THREADS)
+    L.append(scalar_elem("        ", "e"))
+    L.append("      }\n      continue;\n    }")
+    for i in range(n_in):
+        if not scalar_in[i]:
+            L.append(f"    Pack<T{i}, E> a{i}[U];")
+    L.append("#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const long long e = col0 + (long long)(u * %d + tid) * E;" % THREADS)
+    for i in range(n_in):
+        if not scalar_in[i]:
+            L.append(f"      fload_vec<T{i}, E>(a{i}[u], plan.op[{n_out + i}], off{n_out + i}, e);")
+    L.append("    }\n#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const long long e = col0 + (long long)(u * %d + tid) * E;" % THREADS)
+    for j, (v, _) in enumerate(outs):
+        L.append(f"      Pack<T{v}, E> r{j};")
+    args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[u][i_]" for i in range(n_in)] +
+                     [f"r{j}[i_]" for j in range(n_out)])
+    L.append(f"#pragma unroll\n      for (int i_ = 0; i_ < E; ++i_) body({args});")
+    for j, (v, _) in enumerate(outs):
+        L.append(f"      st_bytes<sizeof(T{v}) * E>(plan.op[{j}].ptr + off{j} + e * (long long)sizeof(T{v}), r{j}.raw);")
+    L.append("    }\n  }\n}")
+
+    # ---- strided kernel (coalesced element accesses, batches of B, store-aligned rows)
+    v0 = outs[0][0]
+    L.append(f'extern "C" __global__ void __launch_bounds__({THREADS}) fused_{h}_str(const __grid_constant__ FPlan plan)\n{{')
+    L.append(head)
+    L.append(f"""    constexpr int N = E * U;
+    long long shift = 0;
+    if (plan.out_pad != 0)
+      shift = static_cast<long long>((reinterpret_cast<unsigned long long>(plan.op[0].ptr + off0) & 127ull) / sizeof(T{v0}));
+    const long long tbase = col0 - shift;
+#pragma unroll 1
+    for (int j0 = 0; j0 < N; j0 += B) {{""")
+    for i in range(n_in):
+        if not scalar_in[i]:
+            L.append(f"      Pack<T{i}, 1> a{i}[B];")
+    L.append("#pragma unroll\n      for (int j = 0; j < B; ++j) {\n        const long long e = tbase + (long long)(j0 + j) * %d + tid;\n        if (j0 + j < N && e >= 0 && e < plan.inner) {" % THREADS)
+    for i in range(n_in):
+        if not scalar_in[i]:
+            L.append(f"          fload_one<T{i}>(a{i}[j], plan.op[{n_out + i}], off{n_out + i}, e);")
+    L.append("        }\n      }\n#pragma unroll\n      for (int j = 0; j < B; ++j) {\n        const long long e = tbase + (long long)(j0 + j) * %d + tid;\n        if (j0 + j < N && e >= 0 && e < plan.inner) {" % THREADS)
+    for j, (v, _) in enumerate(outs):
+        L.append(f"          Pack<T{v}, 1> r{j};")
+    args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[j][0]" for i in range(n_in)] +
+                     [f"r{j}[0]" for j in range(n_out)])
+    L.append(f"          body({args});")
+    for j, (v, _) in enumerate(outs):
+        L.append(f"          st_bytes<sizeof(T{v})>(plan.op[{j}].ptr + off{j} + e * plan.op[{j}].inner_stride, r{j}.raw);")
+    L.append("        }\n      }\n    }\n  }\n}")
+    return "\n".join(L) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------
+# launch
+# ---------------------------------------------------------------------------------------------
+def _canonical(shape, strides_list):
+    """cnb ew_make_plan in Python: drop unit dims, order by the first operand's |stride|, merge
+    jointly contiguous dims.  Returns [(extent, [stride per operand])] slowest first."""
+    dims = [d for d in range(len(shape)) if shape[d] != 1]
+    if not dims:
+        return [(1, [0] * len(strides_list))]
+    dims.sort(key=lambda d: -abs(strides_list[0][d]))
+    merged = [[shape[dims[0]], [s[dims[0]] for s in strides_list]]]
+    for d in dims[1:]:
+        n = shape[d]
+        st = [s[d] for s in strides_list]
+        last = merged[-1]
+        if all(last[1][k] == n * st[k] for k in range(len(st))):
+            last[0] *= n
+            last[1] = st
+        else:
+            merged.append([n, st])
+    return [(n, st) for n, st in merged]
+
+
+def _launch(entry, shape, out_windows, in_windows, ntasks: int) -> bool:
+    from .runtime import runtime
+
+    k_vec, k_str, plan_cls, geo, _ = entry
+    windows = list(out_windows) + list(in_windows)
+    dims = _canonical(shape, [w.strides for w in windows])
+    if len(dims) > 2:
+        return False
+    inner, inner_st = dims[-1]
+    rows, row_st = (dims[0] if len(dims) == 2 else (1, [0] * len(windows)))
+    sizes = geo["out_sizes"] + geo["in_sizes"]
+    E = geo["E"]
+    n_out = len(out_windows)
+    for w in in_windows:
+        if w.buffer.ready_event is not None:
+            runtime.wait_ready(w.buffer)
+    plan = plan_cls()
+    vec = True
+    algo = 0
+    for k, w in enumerate(windows):
+        ptr = w.buffer.ptr + w.offset
+        plan.op[k].ptr = ptr
+        plan.op[k].inner_stride = inner_st[k]
+        plan.op[k].row_stride = row_st[k]
+        size = sizes[k]
+        bcast = inner_st[k] == 0 and k >= n_out
+        align = size if bcast else min(16, size * E)
+        if not bcast and inner_st[k] != size and inner != 1:
+            vec = False
+        if ptr % align or row_st[k] % align:
+            vec = False
+        distinct = (inner if inner_st[k] != 0 else 1) * (rows if row_st[k] != 0 else 1)
+        algo += distinct * size
+    tile = geo["TILE"]
+    out_pad = 0
+    if not vec and inner_st[0] == sizes[0] and sizes[0] < 128:
+        out_pad = 128 // sizes[0] - 1
+    plan.inner, plan.rows = inner, rows
+    plan.tiles_per_row = (inner + out_pad + tile - 1) // tile
+    plan.num_tiles = plan.tiles_per_row * rows
+    plan.vec, plan.out_pad = int(vec), out_pad
+    _lib.check(runtime.lib.cnb_launch_fused(k_vec if vec else k_str, ctypes.byref(plan),
+                                            ctypes.sizeof(plan), plan.num_tiles, inner * rows, algo,
+                                            ntasks, runtime.stream))
+    stats["fused_launches"] += 1
+    stats["fused_tasks"] += ntasks
+    return True
+
+
+# ---------------------------------------------------------------------------------------------
+# tracing without a device (used by __graft_entry__.build to pre-compile benchmark chains)
+# ---------------------------------------------------------------------------------------------
+def trace_only(fn) -> int:
+    """Run `fn()` with the runtime in dry-run mode: arrays are created lazily, elementwise tasks
+    are captured, every chain that forms is generated + compiled into the disk cache, nothing is
+    launched.  Returns the number of kernels compiled."""
+    global _mode
+    from .runtime import runtime
+
+    flush()
+    before = stats["compiled"]
+    old_mode, old_dry = _mode, runtime.dry_run
+    _mode, runtime.dry_run = "always", True
+    try:
+        fn()
+        flush()
+    finally:
+        flush()
+        _mode, runtime.dry_run = old_mode, old_dry
+    return stats["compiled"] - before

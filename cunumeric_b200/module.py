@@ -132,6 +132,14 @@ def map_chunks(fn, inputs, outputs, chunk: int) -> None:
             f.wait()
 
 
+def flush() -> None:
+    """Launch every captured-but-not-yet-issued elementwise task (fusion.py).  Reading a value,
+    copying to the host and `synchronize()` do this implicitly."""
+    from . import fusion
+
+    fusion.flush()
+
+
 def synchronize() -> None:
     runtime.synchronize()
 

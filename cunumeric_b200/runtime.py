@@ -22,24 +22,36 @@ class DeviceBuffer:
     counting can be handed out again immediately: stream order already serialises the old reader
     and the new writer); misses go to the stream-ordered CUDA pool."""
 
-    __slots__ = ("ptr", "base", "nbytes", "_runtime", "ready_event", "__weakref__")
+    __slots__ = ("_ptr", "base", "nbytes", "_runtime", "ready_event", "users", "__weakref__")
 
     def __init__(self, runtime: "Runtime", nbytes: int) -> None:
         self._runtime = runtime
         self.nbytes = max(int(nbytes), 1)
-        self.base, self.ptr = runtime._take_block(self.nbytes)
+        # The block is taken on first use: a temporary that only ever lives inside a fused chain
+        # (fusion.py) never touches memory and never allocates.
+        self.base = self._ptr = None
         # set while an asynchronous H2D copy (on the copy stream) is still filling this buffer; the
         # compute stream waits for it the first time the buffer is used by a task
         self.ready_event = None
+        # number of live Store windows onto this buffer (fusion.py: an output nobody can observe
+        # any more is not written)
+        self.users = 0
+
+    @property
+    def ptr(self) -> int:
+        if self._ptr is None:
+            self._runtime.ensure_initialized()
+            self.base, self._ptr = self._runtime._take_block(self.nbytes)
+        return self._ptr
 
     def __del__(self) -> None:
         try:
             rt = self._runtime
-            if rt is not None and rt.lib is not None and self.ptr:
-                rt._give_block(self.base, self.ptr, self.nbytes)
+            if rt is not None and rt.lib is not None and self._ptr:
+                rt._give_block(self.base, self._ptr, self.nbytes)
         except Exception:
             pass
-        self.ptr = None
+        self._ptr = None
 
 
 class PinnedBuffer:
@@ -82,6 +94,8 @@ class Runtime:
         self._cached_bytes = 0
         self._cache_limit = None
         self._colour = 0
+        # dry run (fusion.trace_only): arrays are created and tasks captured, nothing touches a device
+        self.dry_run = False
 
     # ------------------------------------------------------------------ lifecycle
     def ensure_initialized(self) -> None:
@@ -112,13 +126,17 @@ class Runtime:
         return int(self.lib.cnb_launch_count())
 
     def synchronize(self) -> None:
+        from . import fusion
+
+        fusion.flush()
         self.ensure_initialized()
         _lib.check(self.lib.cnb_stream_synchronize(self.stream))
 
     # ------------------------------------------------------------------ memory
     def allocate(self, nbytes: int) -> DeviceBuffer:
-        self.ensure_initialized()
-        return DeviceBuffer(self, nbytes)
+        if not self.dry_run:
+            self.ensure_initialized()  # fail loudly without a device: there is no CPU fallback
+        return DeviceBuffer(self, nbytes)  # the block itself is taken when `.ptr` is first read
 
     # Large blocks are "coloured": each gets a different sub-2-MiB start offset, so that the
     # operands of one task are never congruent modulo a large power of two.  Power-of-two sized
@@ -238,7 +256,8 @@ class Runtime:
                 self._scalar_cache.clear()
             buf = self.allocate(value.nbytes)
             staged = np.ascontiguousarray(value)
-            self.copy_h2d(buf.ptr, staged)
+            if not self.dry_run:
+                self.copy_h2d(buf.ptr, staged)
             # the H2D of a pageable source is staged by the driver before returning
             self._scalar_cache[key] = buf
         return buf

@@ -3,12 +3,14 @@ reference gets from legate.core stores: slice, project, promote, t
 A Store never owns arithmetic; DeferredArray turns stores into cnb_store_t descriptors."""
 from __future__ import annotations
 
+import math
 from typing import Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
 from .config import MAX_DIM, dtype_code
+from . import fusion
 from .runtime import DeviceBuffer, runtime
 
 
@@ -22,7 +24,7 @@ def c_strides(shape: Sequence[int], itemsize: int) -> Tuple[int, ...]:
 
 
 class Store:
-    __slots__ = ("buffer", "dtype", "shape", "strides", "offset")
+    __slots__ = ("buffer", "dtype", "shape", "strides", "offset", "_win", "_size")
 
     def __init__(self, buffer: DeviceBuffer, dtype, shape, strides=None, offset: int = 0) -> None:
         self.buffer = buffer
@@ -31,14 +33,30 @@ class Store:
         self.strides = (c_strides(self.shape, self.dtype.itemsize) if strides is None
                         else tuple(int(s) for s in strides))
         self.offset = int(offset)
+        self._win = None    # fusion._Window of this (immutable) store, built on first capture
+        self._size = None
+        buffer.users += 1
+
+    def __del__(self) -> None:
+        try:
+            self.buffer.users -= 1
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ construction
     @staticmethod
     def empty(shape, dtype) -> "Store":
         dtype = np.dtype(dtype)
         shape = tuple(int(s) for s in shape)
-        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        return Store(runtime.allocate(nbytes), dtype, shape)
+        size = math.prod(shape)
+        # fast constructor: everything is already normalised
+        st = object.__new__(Store)
+        st.buffer = buffer = runtime.allocate(size * dtype.itemsize)
+        st.dtype, st.shape, st.offset = dtype, shape, 0
+        st.strides = c_strides(shape, dtype.itemsize)
+        st._win, st._size = None, size
+        buffer.users += 1
+        return st
 
     @staticmethod
     def from_scalar(value: np.ndarray) -> "Store":
@@ -53,10 +71,15 @@ class Store:
 
     @property
     def size(self) -> int:
-        return int(np.prod(self.shape, dtype=np.int64))
+        if self._size is None:
+            self._size = math.prod(self.shape)
+        return self._size
 
     @property
     def ptr(self) -> int:
+        # every consumer of device memory goes through here: pending fused chains run first
+        if fusion.pending():
+            fusion.flush()
         return self.buffer.ptr + self.offset
 
     @property

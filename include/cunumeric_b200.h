@@ -250,6 +250,20 @@ const char* cnb_last_error(void);
 const char* cnb_version(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused elementwise chains (hooks in the reference would sit at
+ * deferred.py:3139,3302 where UNARY_OP / BINARY_OP tasks are built).  The host layer captures a
+ * chain of elementwise tasks over one iteration space, composes the SAME device functors the
+ * per-task kernels use into one generated kernel (cunumeric_b200/fusion.py), compiles it for
+ * sm_100a and runs it through these three calls.  `plan` is the generated kernel's single
+ * by-value parameter (layout defined by the generator); `tag` is the CNB_OP_* recorded in the
+ * launch trace (CNB_OP_FUSED). */
+#define CNB_OP_FUSED 1000
+int cnb_module_load(const void* image, size_t bytes, void** module);
+int cnb_module_get_kernel(void* module, const char* name, void** kernel);
+int cnb_launch_fused(void* kernel, const void* plan, size_t plan_bytes, int64_t num_tiles,
+                     int64_t elements, int64_t algorithmic_bytes, int32_t ntasks, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU exchange (one process per GPU).  In the reference these steps are implicit Legion
  * copies / future-map folds; here they are explicit, stream-ordered NCCL calls.
  * ------------------------------------------------------------------------------------------- */

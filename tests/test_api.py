@@ -30,11 +30,24 @@ def test_black_scholes_matches_oracle_and_numpy():
     from cunumeric_b200.workloads import black_scholes, black_scholes_inputs
     from oracle import refnp
 
+    from cunumeric_b200 import fusion
+
     S, X, T = black_scholes_inputs(50000, np.float32, seed=3)
-    launches = cn.runtime.launch_count() if cn.runtime.lib else 0
-    c, p = black_scholes(cn.array(S), cn.array(X), cn.array(T), 0.02, 0.3)
+    old = fusion.set_mode("0")  # op-by-op: one kernel per task, scalars converted on the host
+    try:
+        dS, dX, dT = cn.array(S), cn.array(X), cn.array(T)
+        launches = cn.runtime.launch_count()
+        c, p = black_scholes(dS, dX, dT, 0.02, 0.3)
+        assert cn.runtime.launch_count() - launches == 63
+        fusion.set_mode("always")  # the same program as ONE fused kernel, bit-identical
+        launches = cn.runtime.launch_count()
+        cf, pf = black_scholes(dS, dX, dT, 0.02, 0.3)
+        cn.flush()
+        assert cn.runtime.launch_count() - launches == 1
+        assert np.array_equal(cf.__array__(), c.__array__()) and np.array_equal(pf.__array__(), p.__array__())
+    finally:
+        fusion.set_mode(old)
     assert c.dtype == np.float32 and p.dtype == np.float32
-    assert cn.runtime.launch_count() - launches == 63  # one kernel per task, scalars on the host
     co, po = black_scholes(refnp.array(S), refnp.array(X), refnp.array(T), 0.02, 0.3, xp=refnp)
     cn_, pn = black_scholes(S, X, T, 0.02, 0.3, xp=np)
     for got, ora, npy in ((c, co.a, cn_), (p, po.a, pn)):

@@ -1,0 +1,253 @@
+"""Lazy fusion of elementwise chains (cunumeric_b200/fusion.py).
+
+CPU part: chains are captured and their kernels generated + compiled with nvcc WITHOUT a device
+(the dry-run tracer `__graft_entry__.build()` uses).  GPU part: every program below is run twice —
+fused (`always`: compile at first sight) and op-by-op (`0`) — and the results must be bit-identical,
+because the fused kernel composes the same device functors with the same rounding points."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import parity_utils as pu
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8)
+
+
+def run_both(program):
+    """program() -> list of cunumeric arrays; returns (fused results, eager results, fused stats)."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    old = fusion.set_mode("always")
+    try:
+        before = dict(fusion.stats)
+        fused = [np.array(x.__array__()) for x in program()]
+        delta = {k: fusion.stats[k] - before[k] for k in before}
+        fusion.set_mode("0")
+        eager = [np.array(x.__array__()) for x in program()]
+    finally:
+        fusion.set_mode(old)
+    return fused, eager, delta
+
+
+def assert_identical(fused, eager):
+    assert len(fused) == len(eager)
+    for f, e in zip(fused, eager):
+        assert f.dtype == e.dtype and f.shape == e.shape
+        assert np.array_equal(_bits(f), _bits(e)), (f.dtype, np.flatnonzero(_bits(f) != _bits(e))[:5])
+
+
+# ------------------------------------------------------------------------------------ CPU
+def test_trace_and_compile_without_a_device(tmp_path, monkeypatch):
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+    from cunumeric_b200.workloads import black_scholes, stencil_init, stencil_run
+
+    if cn.runtime.lib is not None:
+        pytest.skip("runtime already initialised on a device")
+    monkeypatch.setattr(fusion, "_CACHE_DIR", str(tmp_path))
+    fusion._kernels.clear()
+
+    def bs():
+        S, X, T = (cn.empty((1000,), dtype=np.float32) for _ in range(3))
+        out = black_scholes(S, X, T, 0.02, 0.3)
+        cn.flush()
+        return out
+
+    assert fusion.trace_only(bs) == 1
+    (src,) = [f for f in os.listdir(tmp_path) if f.endswith(".cu")]
+    text = open(tmp_path / src).read()
+    assert "63 tasks, 16 inputs, 2 stored outputs" in text  # 61 intermediates stay in registers
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
+
+    def stencil():
+        # lazily allocated grid: the boundary fills are skipped in a dry run
+        g = cn.empty((66, 66), dtype=np.float64)
+        return stencil_run(g, 2)
+
+    # per iteration: [4 ADD + MULTIPLY] fuse; the COPY back into `center` overlaps the shifted
+    # views the chain reads, so it must NOT join the chain
+    n = fusion.trace_only(stencil)
+    assert n == 1
+    texts = [open(tmp_path / f).read() for f in os.listdir(tmp_path) if f.endswith(".cu")]
+    assert any("5 tasks, 6 inputs, 2 stored outputs" in t for t in texts), [t[:120] for t in texts]
+
+
+def test_hazard_rules_dry():
+    """Windows that overlap a chain output through a DIFFERENT window force a flush."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    if cn.runtime.lib is not None:
+        pytest.skip("runtime already initialised on a device")
+    seen = []
+
+    def prog():
+        a = cn.empty((100,), dtype=np.float32)
+        b = a + 1.0          # chain: [t0]
+        c = b * 2.0          # same window of b -> joins: [t0, t1]
+        seen.append(len(fusion._chain.tasks))
+        d = b[1:] + 1.0      # different shape -> flush, new chain [t2]
+        seen.append(len(fusion._chain.tasks))
+        a[10:20] = 3.0       # fill is not elementwise-captured: flushes through Store.ptr in real runs
+        e = cn.empty((99,), dtype=np.float32)
+        f = e + 1.0
+        e[:] = f             # writes the window the chain read through the same window: joins
+        seen.append(len(fusion._chain.tasks))
+        return c, d
+
+    cn.runtime.dry_run = True
+    old = fusion.set_mode("always")
+    try:
+        prog()
+    except RuntimeError:
+        pass  # the fill needs a device; everything before it is what we check
+    finally:
+        fusion._chain = fusion._Chain()
+        fusion.set_mode(old)
+        cn.runtime.dry_run = False
+    assert seen[:2] == [2, 1]
+
+
+# ------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.float16], ids=lambda d: np.dtype(d).name)
+def test_black_scholes_fused_is_bit_identical(dt):
+    import cunumeric_b200 as cn
+    from cunumeric_b200.workloads import black_scholes, black_scholes_inputs
+
+    S, X, T = black_scholes_inputs(100003, np.float32)
+    S, X, T = (v.astype(dt) for v in (S, X, T))
+
+    def prog():
+        return black_scholes(cn.array(S), cn.array(X), cn.array(T), 0.02, 0.3)
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    assert delta["fused_launches"] == 1 and delta["fused_tasks"] == 63
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dt", [(30, np.float64), (301, np.float64), (64, np.float32)])
+def test_stencil_fused_is_bit_identical(n, dt):
+    import cunumeric_b200 as cn
+    from cunumeric_b200.workloads import stencil_init, stencil_run
+
+    def prog():
+        g = stencil_init(n, dt, xp=cn)
+        w = stencil_run(g, 4)
+        return g, w
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    g_np = stencil_init(n, dt, xp=np)
+    w_np = stencil_run(g_np, 4)
+    assert np.array_equal(fused[0], g_np) and np.array_equal(fused[1], w_np)
+    # 4 iterations x [4 ADD + MULTIPLY]; the boundary writes of stencil_init may add one chain
+    assert delta["fused_launches"] in (4, 5)
+
+
+@pytest.mark.gpu
+def test_inplace_views_and_hazards():
+    import cunumeric_b200 as cn
+
+    rng = pu.rng_for("fusion-hazards")
+    a0 = rng.normal(size=(257, 130))
+    b0 = rng.normal(size=(257, 130))
+
+    def prog():
+        a, b = cn.array(a0), cn.array(b0)
+        a += b                      # in place: external read and final store of the same window
+        a *= 2.0
+        c = a - b
+        a[1:] = a[:-1] + c[1:]      # shifted self-overlap: needs the copy + a flush
+        d = a[:, ::2] * b[:, 1::2]  # strided inner dim -> strided kernel
+        e = cn.where(d > 0.5, d, -d) + a[:, :65]
+        a[0, :] = 1.0               # scalar write into a row between chains
+        f = (a.T + 1.0) * b.T       # uniformly transposed operands
+        row = a[3] * 2.0
+        g = b + row                 # (130,) broadcast over rows
+        return a, c, d, e, f, g
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    assert delta["fused_launches"] >= 3
+
+
+@pytest.mark.gpu
+def test_mixed_dtypes_conversions_and_dead_temporaries():
+    import cunumeric_b200 as cn
+
+    rng = pu.rng_for("fusion-mixed")
+    x0 = rng.normal(size=70001).astype(np.float32)
+    i0 = rng.integers(-50, 50, size=70001).astype(np.int32)
+
+    def prog():
+        x, i = cn.array(x0), cn.array(i0)
+        y = x.astype(np.float64) * 3.0 + i           # CONVERT f32->f64, CONVERT i32->f64 inside
+        m = (y > 1.0) & (i != 0)                      # compares -> bool, logical/bitwise on bool
+        z = cn.where(m, y, 0.0)
+        h = (x * x).astype(np.float16)
+        k = i // 7 + i % 5 - (i << 1)
+        q = cn.sqrt(cn.absolute(y)) + cn.exp(-cn.absolute(x))
+        c = (x + 1j * x).astype(np.complex64) * (2 - 1j)
+        s = float((z * 2.0).sum())                    # a reduction consumes a chain result
+        t = z + s
+        return y, m, z, h, k, q, c, t
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    assert delta["fused_launches"] >= 1
+
+
+@pytest.mark.gpu
+def test_rewriting_the_same_output_and_3d_fallback():
+    import cunumeric_b200 as cn
+
+    rng = pu.rng_for("fusion-rewrite")
+    a0 = rng.normal(size=(5, 7, 9, 11)).astype(np.float32)
+
+    def prog():
+        a = cn.array(a0)
+        out = cn.empty(a.shape, dtype=np.float32)
+        cn.add(a, 1.0, out=out)
+        cn.multiply(out, out, out=out)          # reads and rewrites the same window
+        cn.subtract(out, a, out=out)
+        v = a[:, 1:, :, 2:] * 2.0 + a[:, :-1, :, :-2]   # 4-D windows that do not merge to 2-D
+        w = v - 1.0
+        return out, v, w
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+
+
+@pytest.mark.gpu
+def test_default_mode_compiles_on_second_sighting(tmp_path, monkeypatch):
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    monkeypatch.setattr(fusion, "_CACHE_DIR", str(tmp_path))
+    x0 = np.linspace(0, 1, 50000, dtype=np.float32)
+    old = fusion.set_mode("1")
+    try:
+        results = []
+        for rep in range(3):
+            before = dict(fusion.stats)
+            x = cn.array(x0)
+            y = cn.tanh(x * 3.0 + 0.25) - x / 7.0
+            results.append(np.array(y.__array__()))
+            d = {k: fusion.stats[k] - before[k] for k in before}
+            if rep == 0:
+                assert d["fused_launches"] == 0 and d["replayed_tasks"] == 5
+            else:
+                assert d["fused_launches"] == 1, d
+        assert np.array_equal(results[0], results[1]) and np.array_equal(results[1], results[2])
+    finally:
+        fusion.set_mode(old)

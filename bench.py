@@ -83,7 +83,7 @@ class ClockSampler:
     Uses NVML in a background thread (same counters as the recipe's nvidia-smi line, without
     spawning a process that contends for the driver lock while kernels are being launched)."""
 
-    def __init__(self, device: int, period_s: float = 0.05) -> None:
+    def __init__(self, device: int, period_s: float = 0.01) -> None:
         self.device = device
         self.period = period_s
         self.samples = []
@@ -398,6 +398,12 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
     if fused_on:
         elapsed, launches, roofline = timed(True, args.steps, True)
         bytes_per_option = 20  # 3 fp32 inputs + 2 fp32 outputs; 61 intermediates stay in registers
+        if roofline is not None:
+            roofline["limiter"] = ("instruction issue, not HBM: ~173 SASS instructions per option "
+                                   "(4 IEEE divisions, 3 exp, log, sqrt, no FMA contraction — the "
+                                   "bit-parity contract with op-by-op execution); ncu: 80 % of issue "
+                                   "slots busy, DRAM traffic = algorithmic bytes "
+                                   "(profiles/r01_fusion_ncu_summary.md)")
     else:
         elapsed, launches, roofline = obo_elapsed, obo_launches, obo_roofline
         bytes_per_option = BLACK_SCHOLES_BYTES_PER_OPTION_F32

@@ -474,6 +474,10 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
 
 
 def main() -> None:
+    # rank 0 must print exactly one JSON line on stdout: keep NCCL's "NCCL version ..." banner
+    # (NCCL_DEBUG=VERSION in some images) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

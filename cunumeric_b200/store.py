@@ -35,7 +35,8 @@ class Store:
         self.offset = int(offset)
         self._win = None    # fusion._Window of this (immutable) store, built on first capture
         self._size = None
-        buffer.users += 1
+        if buffer is not None:  # (shape-only probes carry no buffer)
+            buffer.users += 1
 
     def __del__(self) -> None:
         try:

@@ -94,7 +94,12 @@ class ClockSampler:
         self._handle = None
         self._max = None
         # NVML initialisation takes ~100 ms and briefly stalls the driver: do it here, outside the
-        # timed region; start() only spawns the polling thread.
+        # timed region; start() only spawns the polling thread.  Only rank 0 samples (its own GPU):
+        # NVML queries take a driver-wide lock, and eight ranks polling at once delay each other's
+        # kernel launches.
+        if int(os.environ.get("RANK", "0")) != 0:
+            self._err = "clocks are sampled on rank 0 only"
+            return
         try:
             import pynvml as nv
 

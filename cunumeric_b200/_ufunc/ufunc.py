@@ -341,6 +341,20 @@ class binary_ufunc(ufunc):
             cls._scalar_cache[key] = hit
         return hit
 
+    _bcast_cache: Dict[Tuple[int, Tuple[int, ...]], Any] = {}
+
+    @classmethod
+    def _broadcast_scalar(cls, base, shape):
+        """stride-0 view of a cached weak scalar, itself cached (the scalar ndarray stays alive in
+        _scalar_cache, so id(base) is stable; both caches are cleared together)"""
+        key = (id(base), shape)
+        hit = cls._bcast_cache.get(key)
+        if hit is None or hit[0] is not base:
+            if len(cls._bcast_cache) > 2048:
+                cls._bcast_cache.clear()
+            hit = cls._bcast_cache[key] = (base, base.broadcast_to(shape))
+        return hit[1]
+
     def _fast_call(self, a, b):
         ndarray = _ndarray_type()
         ta, tb = type(a), type(b)
@@ -373,11 +387,13 @@ class binary_ufunc(ufunc):
             out = DeferredArray(Store.empty(shape, res))
             b1, b2 = t1.base, t2.base
             if b1.shape != shape:
-                b1 = b1.broadcast_to(shape)
+                b1 = self._broadcast_scalar(b1, shape)
             if b2.shape != shape:
-                b2 = b2.broadcast_to(shape)
+                b2 = self._broadcast_scalar(b2, shape)
             out.binary_op_prepared(self._op_code, b1, b2)
-            return ndarray(shape, thunk=out)
+            result = object.__new__(ndarray)
+            result._thunk, result._writeback = out, None
+            return result
         result = ndarray(shape, res, inputs=(x1, x2))
         result._thunk.binary_op(self._op_code, t1, t2, True, ())
         return result

@@ -163,10 +163,10 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
     for n, st in zip(shape, lhs.strides):
         if st == 0 and n > 1:
             return False
-    if lhs.dtype not in _PLAIN_DTYPES:
+    if lhs.dtype.kind == "V":  # Argval structs
         return False
     for r in rhs:
-        if r.shape != shape or r.dtype not in _PLAIN_DTYPES:
+        if r.shape != shape or r.dtype.kind == "V":
             return False
     c = _chain
     if c.tasks and (c.shape != shape or len(c.tasks) >= MAX_TASKS or
@@ -304,22 +304,63 @@ def _replay(c: _Chain, tasks: List[_Task]) -> None:
         return
     from . import deferred
 
+    last_use = {}
+    for i, t in enumerate(tasks):
+        for v in t.ins:
+            last_use[v] = i
     produced = {}
-    for t in tasks:
+    for i, t in enumerate(tasks):
         ins = []
         for v in t.ins:
             w = c.ext[v] if c.ext[v] is not None else produced[v]
             ins.append(w.store())
         deferred.launch_elementwise(t.kind, t.op, t.nan_op, t.window.store(), ins)
+        del ins
         produced[t.out] = t.window
+        # a dead temporary (no live Store, no later reader in the chain) gives its block back right
+        # away, as eager execution would: replaying a long chain must not hold every intermediate
+        for v in set(t.ins):
+            if last_use.get(v) == i and c.ext[v] is None:
+                w = produced[v]
+                bid = id(w.buffer)
+                # ... and only if this window is the chain's sole handle on the allocation
+                if w.buffer.users == 0 and len(c.w_by_buf.get(bid, ())) == 1 and \
+                        bid not in c.r_by_buf and c.written[w.key][0] == v:
+                    w.buffer.release()
     stats["replayed_tasks"] += len(tasks)
 
 
 # ---------------------------------------------------------------------------------------------
 # kernel lookup / generation / compilation
 # ---------------------------------------------------------------------------------------------
+_GENERATOR_VERSION = 3
+_src_tag: List[str] = []
+
+
+def _source_tag() -> str:
+    """Digest of everything a generated kernel is built from besides its signature: the functor /
+    engine headers and this generator.  Part of every cache key, so a cubin compiled against older
+    headers is never reused."""
+    if not _src_tag:
+        h = hashlib.sha1(str(_GENERATOR_VERSION).encode())
+        for name in ("cnb_common.cuh", "cnb_elementwise.cuh", "ops_math.cuh", "ops_binary.cuh",
+                     "ops_unary.cuh", "ops_convert.cuh"):
+            try:
+                with open(os.path.join(_CSRC, name), "rb") as f:
+                    h.update(f.read())
+            except OSError:
+                h.update(name.encode())
+        try:
+            with open(os.path.join(_INCLUDE, "cunumeric_b200.h"), "rb") as f:
+                h.update(f.read())
+        except OSError:
+            pass
+        _src_tag.append(h.hexdigest())
+    return _src_tag[0]
+
+
 def _hash(sig) -> str:
-    return hashlib.sha1(repr(sig).encode()).hexdigest()[:20]
+    return hashlib.sha1((_source_tag() + repr(sig)).encode()).hexdigest()[:20]
 
 
 def _lookup(sig):

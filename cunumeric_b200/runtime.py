@@ -44,11 +44,17 @@ class DeviceBuffer:
             self.base, self._ptr = self._runtime._take_block(self.nbytes)
         return self._ptr
 
+    def release(self) -> None:
+        """Give the block back now (a later `.ptr` would take a fresh one).  Only for buffers nobody
+        can observe any more."""
+        rt = self._runtime
+        if rt is not None and rt.lib is not None and self._ptr:
+            rt._give_block(self.base, self._ptr, self.nbytes)
+        self.base = self._ptr = None
+
     def __del__(self) -> None:
         try:
-            rt = self._runtime
-            if rt is not None and rt.lib is not None and self._ptr:
-                rt._give_block(self.base, self._ptr, self.nbytes)
+            self.release()
         except Exception:
             pass
         self._ptr = None

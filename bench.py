@@ -34,7 +34,7 @@ UNIT = "options/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="own", choices=["own", "reference"])
     p.add_argument("--workload", default="black_scholes", choices=["black_scholes", "stencil"])
@@ -44,6 +44,8 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=10_000_000,
                    help="options in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--e2e-chunks", type=int, default=8,
+                   help="chunks per step of the e2e leg (upload / compute / download pipeline)")
     p.add_argument("--fusion", choices=["on", "off"], default="on",
                    help="on: elementwise chains run as fused kernels (default product path); "
                         "off: one kernel per task")
@@ -422,7 +424,7 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
         call_h, put_h = cn.pinned_empty(n, np.float32), cn.pinned_empty(n, np.float32)
         e2e_steps = max(2, min(args.steps, 5))
 
-        chunk = max(1, n // 8)
+        chunk = max(1, n // args.e2e_chunks)
 
         def e2e_step():
             # host buffers in, host buffers out: upload of chunk i+1, kernels of chunk i and

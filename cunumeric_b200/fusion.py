@@ -398,15 +398,17 @@ def _compile(sig, h: str, path: str) -> bool:
         return False
     os.makedirs(_CACHE_DIR, exist_ok=True)
     src = generate_source(sig, h)
-    src_path = os.path.join(_CACHE_DIR, f"fused_{h}.cu")
-    with open(src_path, "w") as f:
+    # private temporaries, atomic renames: the ranks of one job may compile the same chain at once
+    fd, tmp_src = tempfile.mkstemp(suffix=".cu", dir=_CACHE_DIR)
+    with os.fdopen(fd, "w") as f:
         f.write(src)
     fd, tmp = tempfile.mkstemp(suffix=".cubin", dir=_CACHE_DIR)
     os.close(fd)
     cmd = [exe, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
            "-fmad=false", "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177",
-           "-I", _CSRC, "-I", _INCLUDE, "-cubin", "-o", tmp, src_path]
+           "-I", _CSRC, "-I", _INCLUDE, "-cubin", "-o", tmp, tmp_src]
     res = subprocess.run(cmd, capture_output=True, text=True)
+    os.replace(tmp_src, os.path.join(_CACHE_DIR, f"fused_{h}.cu"))
     if res.returncode != 0:
         os.unlink(tmp)
         with open(os.path.join(_CACHE_DIR, f"fused_{h}.err"), "w") as f:

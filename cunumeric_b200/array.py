@@ -446,6 +446,42 @@ class ndarray:
             return out
         return result
 
+    def var(self, axis=None, dtype=None, out=None, ddof: int = 0, keepdims: bool = False):
+        """array.py:3234-3323: two passes — the mean first, then <(x-mu)^2> directly (VARIANCE as one
+        scalar reduction when the result is a scalar, else `delta = x - mu` + SUM_SQUARES along the
+        axis) — and a division by (count - ddof)."""
+        if axis is not None and not isinstance(axis, (int, np.integer)):
+            raise NotImplementedError("cunumeric.var only supports int types for `axis` currently")
+        if self.dtype.kind == "c":
+            raise NotImplementedError("var of complex arrays is not supported")
+        if dtype is None:
+            dtype = np.dtype(np.float64) if self.dtype.kind in "biu" else self.dtype
+        dtype = np.dtype(dtype)
+        src = self if self.dtype == dtype else self._astype(dtype)
+        mu = src.mean(axis=axis, dtype=dtype, keepdims=True)
+        if axis is None:
+            count, others = self.size, 1
+        else:
+            ax = int(axis) % max(self.ndim, 1)
+            count = self.shape[ax]
+            others = self.size // max(count, 1) if count else 0
+        if axis is None or others == 1:
+            mu_host = np.asarray(mu.__array__()).reshape(())  # the task takes mu as a scalar future
+            result = ndarray._perform_unary_reduction(UnaryRedCode.VARIANCE, src, axis=axis,
+                                                      dtype=dtype, keepdims=keepdims,
+                                                      args=(mu_host,))
+        else:
+            delta = src - mu
+            result = ndarray._perform_unary_reduction(UnaryRedCode.SUM_SQUARES, delta, axis=axis,
+                                                      dtype=dtype, keepdims=keepdims)
+        from . import _ufunc
+
+        result = _ufunc.true_divide(result, np.array(count - ddof, dtype=dtype))
+        if out is not None:
+            out._thunk.convert(result._thunk)
+            return out
+        return result
+
     @classmethod
     def _perform_unary_reduction(cls, op: UnaryRedCode, src: "ndarray", axis: Any = None,
                                  dtype=None, res_dtype=None, out: Optional["ndarray"] = None,

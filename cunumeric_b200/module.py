@@ -244,6 +244,12 @@ def mean(a, axis=None, dtype=None, out=None, keepdims=False):
     return convert_to_cunumeric_ndarray(a).mean(axis=axis, dtype=dtype, out=out, keepdims=keepdims)
 
 
+def var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
+    """module.py:7608 -> ndarray.var."""
+    return convert_to_cunumeric_ndarray(a).var(axis=axis, dtype=dtype, out=out, ddof=ddof,
+                                               keepdims=keepdims)
+
+
 def count_nonzero(a, axis=None):
     a = convert_to_cunumeric_ndarray(a)
     return ndarray._perform_unary_reduction(UnaryRedCode.COUNT_NONZERO, a, axis=axis,

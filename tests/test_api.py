@@ -225,3 +225,27 @@ def test_async_copies_and_map_chunks():
     cn.map_chunks(lambda a, b: (a + b, cn.sqrt(a) * b), (xh, yh), (o1, o2), chunk=70_001)
     assert np.array_equal(o1, xh + yh)
     assert np.allclose(o2, np.sqrt(xh) * yh, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32], ids=lambda d: np.dtype(d).name)
+def test_var_matches_numpy(dt):
+    """array.py:3234-3323 / tests/integration/test_stats.py: VARIANCE as one scalar reduction,
+    `x - mu` + SUM_SQUARES along an axis, ddof, keepdims."""
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(21)
+    a = (rng.normal(size=(37, 53)) * 5 + 3).astype(dt)
+    A = cn.array(a)
+    tol = dict(rtol=2e-5, atol=1e-6) if dt == np.float32 else dict(rtol=1e-12, atol=1e-12)
+    assert np.allclose(float(A.var()), a.var(), **tol)
+    assert np.allclose(float(cn.var(A, ddof=1)), a.var(ddof=1), **tol)
+    for axis in (0, 1):
+        got = A.var(axis=axis).__array__()
+        assert got.shape == a.var(axis=axis).shape
+        assert np.allclose(got, a.var(axis=axis), **tol)
+        got = A.var(axis=axis, ddof=1, keepdims=True).__array__()
+        assert np.allclose(got, a.var(axis=axis, ddof=1, keepdims=True), **tol)
+    v = cn.array(a[:, 0].copy())
+    assert np.allclose(float(v.var(axis=0)), a[:, 0].var(), **tol)  # 1-D: the scalar-reduction path
+    with pytest.raises(NotImplementedError):
+        A.var(axis=(0, 1))

@@ -174,6 +174,7 @@ class unary_ufunc(ufunc):
         self._nin, self._nout = len(in_ty), len(out_ty)
         self._op_code = op_code
         self._resolution_cache: Dict[np.dtype, np.dtype] = {}
+        self._fast_types: Dict[str, np.dtype] = {}
         self._overrides = overrides
 
     def _resolve_dtype(self, arr, precision_fixed: bool):
@@ -196,8 +197,32 @@ class unary_ufunc(ufunc):
         self._resolution_cache[arr.dtype] = to_dtype
         return arr._astype(to_dtype, temporary=True), np.dtype(self._types[to_dtype.char])
 
+    def _fast_call(self, x):
+        """`ufunc(array)` whose dtype is in the type table: same result as the general path."""
+        ndarray = _ndarray_type()
+        if type(x) is not ndarray or x.ndim == 0:
+            return NotImplemented
+        t = x._thunk
+        if type(t) is not DeferredArray or not _single_gpu():
+            return NotImplemented
+        c = x.dtype.char
+        res = self._fast_types.get(c)
+        if res is None:
+            if c not in self._types:
+                return NotImplemented
+            res = self._fast_types[c] = np.dtype(self._types[c])
+        out = DeferredArray(Store.empty(x.shape, res))
+        out.unary_op_prepared(self._overrides.get(c, self._op_code), t.base)
+        result = object.__new__(ndarray)
+        result._thunk, result._writeback = out, None
+        return result
+
     def __call__(self, *args: Any, out=None, where: Any = True, casting: str = "same_kind",
                  order: str = "K", dtype=None, **kwargs: Any):
+        if out is None and where is True and dtype is None and len(args) == 1 and not kwargs:
+            fast = self._fast_call(args[0])
+            if fast is not NotImplemented:
+                return fast
         (x,), (out,), out_shape, where = self._prepare_operands(*args, out=out, where=where)
         precision_fixed = False
         if dtype is not None:

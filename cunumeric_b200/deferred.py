@@ -277,6 +277,15 @@ class DeferredArray:
         _lib.check(runtime.lib.cnb_binary_op(int(op_code), ctypes.byref(d_out), ctypes.byref(d1),
                                              ctypes.byref(d2), _vp(extra), runtime.stream))
 
+    def unary_op_prepared(self, op_code: int, rhs: Store) -> None:
+        """unary_op for a freshly allocated output of the operand's shape (the ufunc fast path)."""
+        lhs = self.base
+        if fusion.capture("U", int(op_code), lhs, (rhs,)):
+            return
+        d_out, d_in = lhs.descriptor(), rhs.descriptor()
+        _lib.check(runtime.lib.cnb_unary_op(int(op_code), ctypes.byref(d_out), None,
+                                            ctypes.byref(d_in), None, runtime.stream))
+
     def binary_op_prepared(self, op_code: int, rhs1: Store, rhs2: Store) -> None:
         """binary_op for a freshly allocated output and operands already broadcast to its shape
         (the ufunc fast path): nothing to replicate, no aliasing to resolve, no extra scalars."""

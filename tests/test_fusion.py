@@ -116,6 +116,84 @@ def test_hazard_rules_dry():
     assert seen[:2] == [2, 1]
 
 
+def _dry(prog):
+    """Run prog() with capture on and no device; returns the chains (task kinds, live outputs) that
+    were flushed, in order."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    if cn.runtime.lib is not None:
+        pytest.skip("runtime already initialised on a device")
+    flushed = []
+    orig = fusion._run_chain
+
+    def spy(c):
+        live = sum(1 for _, w in c.written.values() if w.buffer.users > 0)
+        flushed.append(([t.kind + str(t.op) for t in c.tasks], live))
+        # no compilation in these tests: the chain bookkeeping is what is checked
+
+    cn.runtime.dry_run = True
+    old = fusion.set_mode("always")
+    fusion._run_chain = spy
+    try:
+        keep = prog()
+        fusion.flush()
+    finally:
+        fusion._run_chain = orig
+        fusion._chain = fusion._Chain()
+        fusion.set_mode(old)
+        cn.runtime.dry_run = False
+    del keep
+    return flushed
+
+
+def test_dead_temporaries_are_not_outputs_dry():
+    import cunumeric_b200 as cn
+
+    def prog():
+        a = cn.empty((1000,), dtype=np.float32)
+        b = cn.empty((1000,), dtype=np.float32)
+        r = cn.sqrt(a * a + b * b) / (a + 1.0)   # 6 tasks, 5 temporaries die immediately
+        return r
+
+    (chain,) = _dry(prog)
+    tasks, live = chain
+    assert len(tasks) == 6 and live == 1
+
+
+def test_inplace_update_joins_but_shifted_write_flushes_dry():
+    import cunumeric_b200 as cn
+
+    def prog():
+        a = cn.empty((64, 64), dtype=np.float64)
+        b = cn.empty((64, 64), dtype=np.float64)
+        a += b                 # reads and writes the same window: joins
+        a *= 2.0               # joins, value of `a` comes from registers
+        c = a[1:, :] + 1.0     # a different window of something the chain wrote: flush first
+        a[:-1, :] = c          # writes a window overlapping the chain's read window a[1:, :]: flush
+        return a, c
+
+    chains = _dry(prog)
+    assert [len(t) for t, _ in chains] == [2, 1, 1]
+
+
+def test_chain_length_and_shape_changes_flush_dry():
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    def prog():
+        x = cn.empty((128,), dtype=np.float32)
+        y = x
+        for _ in range(fusion.MAX_TASKS + 5):
+            y = y + 1.0
+        z = cn.empty((64,), dtype=np.float32) * 2.0   # another shape
+        return y, z
+
+    chains = _dry(prog)
+    assert [len(t) for t, _ in chains] == [fusion.MAX_TASKS, 5, 1]
+    assert all(live == 1 for _, live in chains[1:])
+
+
 # ------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.float16], ids=lambda d: np.dtype(d).name)

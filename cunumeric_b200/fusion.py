@@ -360,7 +360,9 @@ def _source_tag() -> str:
 
 
 def _hash(sig) -> str:
-    return hashlib.sha1((_source_tag() + repr(sig)).encode()).hexdigest()[:20]
+    knobs = "".join(f"{k}={os.environ.get(k, '')};" for k in
+                    ("CNB_FUSED_B", "CNB_FUSED_U", "CNB_FUSED_MINBLOCKS"))
+    return hashlib.sha1((_source_tag() + knobs + repr(sig)).encode()).hexdigest()[:20]
 
 
 def _lookup(sig):
@@ -476,10 +478,12 @@ def _geometry(sig):
     # views of one array (the stencil's five neighbours), whose loads mostly hit L1/L2 but still
     # occupy the thread's load slots, so keep >= 4 elements (~160 B of requests) in flight
     b = max(4, min(16, 64 // max(1, in_bytes)))
+    b = int(os.environ.get("CNB_FUSED_B", b))           # tuning knobs (part of the cache key)
+    u = int(os.environ.get("CNB_FUSED_U", u))
     while e * u < b:
         u += 1
     return {"E": e, "U": u, "B": b, "TILE": THREADS * e * u, "in_sizes": in_sizes,
-            "out_sizes": out_sizes}
+            "out_sizes": out_sizes, "minblocks": int(os.environ.get("CNB_FUSED_MINBLOCKS", "0"))}
 
 
 def generate_source(sig, h: str) -> str:
@@ -609,7 +613,8 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
 
     # ---- strided kernel (coalesced element accesses, batches of B, store-aligned rows)
     v0 = outs[0][0]
-    L.append(f'extern "C" __global__ void __launch_bounds__({THREADS}) fused_{h}_str(const __grid_constant__ FPlan plan)\n{{')
+    lb = f"{THREADS}, {geo['minblocks']}" if geo["minblocks"] else f"{THREADS}"
+    L.append(f'extern "C" __global__ void __launch_bounds__({lb}) fused_{h}_str(const __grid_constant__ FPlan plan)\n{{')
     L.append(head)
     L.append(f"""    constexpr int N = E * U;
     long long shift = 0;

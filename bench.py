@@ -260,12 +260,19 @@ def run_reference(args) -> None:
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "black_scholes fp32 (examples/black_scholes.py), op-by-op",
-                   "options_per_step": n},
+        "config": {"workload": WORKLOAD_BS + "the reference's CPU functors issued op-by-op "
+                                             "(OpenMP, all host cores) on a bounded sample per step",
+                   "execution": "reference-cpu", "options_per_gpu": 100_000_000,
+                   "options_per_step_sampled": n, "tasks_per_step": 63},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# the workload both arms (own / --impl reference) are measured on
+WORKLOAD_BS = ("black_scholes fp32 1e8 options per GPU (examples/black_scholes.py, BASELINE.json "
+               "configs[1]), 63 elementwise tasks per step through the NumPy API; ")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -461,9 +468,7 @@ def run_black_scholes(args, rank: int, world: int, dist) -> None:
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "black_scholes fp32 1e8 options per GPU "
-                                   "(examples/black_scholes.py, BASELINE.json configs[1]), "
-                                   "63 elementwise tasks per step through the NumPy API; " +
+            "config": {"workload": WORKLOAD_BS +
                                    ("the thunk layer captures the chain and runs it as ONE fused "
                                     "kernel (bit-identical to op-by-op; `op_by_op` holds the "
                                     "one-kernel-per-task measurement)" if fused_on else

@@ -100,6 +100,23 @@ def main() -> None:
             if op != "CONTAINS":
                 out[k + "/axis0"] = ref.unary_red(op, a, 0, initial=pre)
                 out[k + "/axis1"] = ref.unary_red(op, a, 1, initial=pre)
+    # BINARY_RED (array_equal / allclose): equal pair, one mismatch, one near-miss per dtype
+    for op in ("EQUAL", "ISCLOSE"):
+        for dt in pu.DTYPES:
+            rng = pu.rng_for("golden-binred", op, dt.name)
+            a = pu.make_input(dt, N, rng, "small")
+            if dt.kind in "fc":
+                a = np.where(np.isnan(a) | np.isinf(a), np.ones_like(a), a)
+            b_same = a.copy()
+            b_diff = a.copy()
+            b_diff[N // 3] = (not b_diff[N // 3]) if dt.kind == "b" else b_diff[N // 3] + dt.type(1)
+            b_near = a.copy()
+            if dt.kind in "fc":
+                b_near = (a * (1 + 3e-4)).astype(dt)
+            k = f"binred/{op}/{dt.name}"
+            out[k + "/a"], out[k + "/b_same"], out[k + "/b_diff"], out[k + "/b_near"] = a, b_same, b_diff, b_near
+            out[k + "/out"] = np.array([ref.binary_red(op, a, b, 1e-3, 1e-5)
+                                        for b in (b_same, b_diff, b_near)])
     path = os.path.join(HERE, "oracle_vectors.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {len(out)} arrays to {path} ({os.path.getsize(path) / 1e6:.2f} MB)")

@@ -221,8 +221,53 @@ def test_oracle_matches_golden_fixtures():
                 got, exp = ref.unary_op(rest[0], a, extra=extra), g[k + "/out"]
             elif kind == "convert":
                 got, exp = ref.convert(g[k + "/a"], np.dtype(rest[2]), rest[0]), g[k + "/out"]
+            elif kind == "binred":
+                got = np.array([ref.binary_red(rest[0], g[k + "/a"], g[k + "/" + b], 1e-3, 1e-5)
+                                for b in ("b_same", "b_diff", "b_near")])
+                exp = g[k + "/out"]
             else:
                 continue
         assert got.tobytes() == exp.tobytes(), k
         checked += 1
     assert checked > 1000
+
+
+# ---- BINARY_RED pinned on the reference's own test vectors ---------------------------------------
+def _binred(op, a, b, **kw):
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.result_type(a, b)
+    shape = np.broadcast_shapes(a.shape, b.shape)
+    a = np.ascontiguousarray(np.broadcast_to(a.astype(dt), shape))
+    b = np.ascontiguousarray(np.broadcast_to(b.astype(dt), shape))
+    return ref.binary_red(op, a, b, **kw)
+
+
+def test_binary_red_known_answers_from_the_reference_tests():
+    """tests/integration/test_array_equal.py:21-75 and test_allclose.py:21-125."""
+    for arr in (1, [1], [[1, 2], [3, 4]]):
+        assert _binred("EQUAL", arr, arr) is True
+    for a, b in ((1, 2), ([1], [2]), ([1, 2], [1, 3])):
+        assert _binred("EQUAL", a, b) is False and _binred("EQUAL", b, a) is False
+    for d1, d2 in ((np.int32, np.float64), (np.float64, np.complex128)):
+        assert _binred("EQUAL", np.array([1, 2, 3], d1), np.array([1, 2, 3], d2)) is True
+    true_pairs = ((0, -1e-8), (1e10, 1.00001e10), (1 + 1j, 1 + 1.00001j), (np.inf, np.inf),
+                  (-np.inf, -np.inf))
+    false_pairs = ((0, -0.000001), (1e10, 1.0001e10), (1 + 1j, 1 + 1.0001j), (np.inf, -np.inf))
+    for a, b in true_pairs:
+        assert _binred("ISCLOSE", a, b) is np.allclose(a, b) is True
+        assert _binred("ISCLOSE", b, a) is np.allclose(b, a) is True
+    for a, b in false_pairs:
+        assert _binred("ISCLOSE", a, b) is np.allclose(a, b) is False
+        assert _binred("ISCLOSE", b, a) is np.allclose(b, a) is False
+    for shape in ((1,), (6,), (1, 1), (2, 3), (2, 3, 4)):
+        size = int(np.prod(shape))
+        for pairs, expect in ((true_pairs[:3], True), (false_pairs[:3], False)):
+            a = np.array([pairs[i % 3][0] for i in range(size)]).reshape(shape)
+            b = np.array([pairs[i % 3][1] for i in range(size)]).reshape(shape)
+            assert _binred("ISCLOSE", a, b) is bool(np.allclose(a, b)) is expect
+    # test_allclose.py:128-150 rtol / atol arguments
+    assert _binred("ISCLOSE", 1e10, 1.0001e10, rtol=1e-3) is True
+    assert _binred("ISCLOSE", 0.0, -1e-6, atol=1e-5) is True
+    # NaN never compares equal / close (equal_nan is unsupported in the reference)
+    assert _binred("EQUAL", [1.0, np.nan], [1.0, np.nan]) is False
+    assert _binred("ISCLOSE", [1.0, np.nan], [1.0, np.nan]) is False

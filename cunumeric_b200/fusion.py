@@ -734,4 +734,16 @@ def trace_only(fn) -> int:
     finally:
         flush()
         _mode, runtime.dry_run = old_mode, old_dry
+        drop_scalar_caches()
     return stats["compiled"] - before
+
+
+def drop_scalar_caches() -> None:
+    """Forget cached 0-d operands.  Scalars created during a dry run were never uploaded, so they
+    must not survive into a run on a device."""
+    from ._ufunc.ufunc import binary_ufunc
+    from .runtime import runtime
+
+    binary_ufunc._scalar_cache.clear()
+    binary_ufunc._bcast_cache.clear()
+    runtime._scalar_cache.clear()

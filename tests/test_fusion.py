@@ -113,6 +113,7 @@ def test_hazard_rules_dry():
         fusion._chain = fusion._Chain()
         fusion.set_mode(old)
         cn.runtime.dry_run = False
+        fusion.drop_scalar_caches()
     assert seen[:2] == [2, 1]
 
 
@@ -143,6 +144,7 @@ def _dry(prog):
         fusion._chain = fusion._Chain()
         fusion.set_mode(old)
         cn.runtime.dry_run = False
+        fusion.drop_scalar_caches()
     del keep
     return flushed
 

@@ -14,11 +14,11 @@ import sim_backend
 def sim(request):
     import cunumeric_b200 as cn
     from cunumeric_b200 import fusion
-    from cunumeric_b200._ufunc.ufunc import binary_ufunc
 
     rt = cn.runtime
     if rt.lib is not None:
         pytest.skip("a real device runtime is live in this process")
+    fusion.drop_scalar_caches()
     lib = sim_backend.SimLib()
     saved = (fusion._lookup, fusion._launch, fusion._mode)
     rt.lib, rt.stream, rt.device = lib, None, 0
@@ -30,9 +30,7 @@ def sim(request):
     finally:
         fusion._chain = fusion._Chain()
         fusion._lookup, fusion._launch, fusion._mode = saved
-        binary_ufunc._scalar_cache.clear()
-        binary_ufunc._bcast_cache.clear()
-        rt._scalar_cache.clear()
+        fusion.drop_scalar_caches()
         rt._free_blocks.clear()
         rt._cached_bytes = 0
         rt._cache_limit = None

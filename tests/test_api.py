@@ -249,3 +249,24 @@ def test_var_matches_numpy(dt):
     assert np.allclose(float(v.var(axis=0)), a[:, 0].var(), **tol)  # 1-D: the scalar-reduction path
     with pytest.raises(NotImplementedError):
         A.var(axis=(0, 1))
+
+
+@pytest.mark.parametrize("mode", ["0", "always"], ids=["op-by-op", "fused"])
+def test_stencil_config_c1_matches_the_reference_arithmetic(mode):
+    """BASELINE.json configs[0]: examples/stencil.py, fp64, N=1000, 100 iterations — the reference's
+    own CPU-runnable case.  Every task is an IEEE add / multiply / copy, so the result must equal
+    op-by-op NumPy (= the reference functors, tests/test_oracle.py::test_jacobi...) bit for bit."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+    from cunumeric_b200.workloads import stencil_init, stencil_run
+
+    old = fusion.set_mode(mode)
+    try:
+        g = stencil_init(1000, np.float64, xp=cn)
+        w = stencil_run(g, 100)
+        got_g, got_w = g.__array__(), w.__array__()
+    finally:
+        fusion.set_mode(old)
+    g_np = stencil_init(1000, np.float64, xp=np)
+    w_np = stencil_run(g_np, 100)
+    assert np.array_equal(got_w, w_np) and np.array_equal(got_g, g_np)

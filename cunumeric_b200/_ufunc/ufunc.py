@@ -350,13 +350,10 @@ class binary_ufunc(ufunc):
 
     @classmethod
     def _weak_scalar(cls, value, dtype):
-        from ..array import ndarray
-        from ..deferred import DeferredArray
-        from ..store import Store
-
         key = (dtype.char, type(value), value)
         hit = cls._scalar_cache.get(key)
         if hit is None:
+            ndarray = _ndarray_type()
             if len(cls._scalar_cache) > 512:
                 cls._scalar_cache.clear()
             with np.errstate(all="ignore"):

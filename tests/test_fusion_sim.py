@@ -19,6 +19,7 @@ def sim(request):
     if rt.lib is not None:
         pytest.skip("a real device runtime is live in this process")
     fusion.drop_scalar_caches()
+    fusion._plan_memo.clear()
     lib = sim_backend.SimLib()
     saved = (fusion._lookup, fusion._launch, fusion._mode)
     rt.lib, rt.stream, rt.device = lib, None, 0
@@ -29,6 +30,7 @@ def sim(request):
         yield lib
     finally:
         fusion._chain = fusion._Chain()
+        fusion._plan_memo.clear()
         fusion._lookup, fusion._launch, fusion._mode = saved
         fusion.drop_scalar_caches()
         rt._free_blocks.clear()

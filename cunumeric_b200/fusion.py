@@ -399,7 +399,11 @@ def _lookup(sig):
         _seen[h] = n
         if _mode != "always" and n < 2:
             return None  # first sighting: run op-by-op, compile when the chain comes back
-        if not _compile(sig, h, path):
+        try:
+            ok = _compile(sig, h, path)
+        except OSError:  # read-only cache directory, no temp space, ...: stay op-by-op
+            ok = False
+        if not ok:
             _kernels[h] = None
             return None
     from .runtime import runtime

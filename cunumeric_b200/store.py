@@ -27,7 +27,9 @@ class Store:
     __slots__ = ("buffer", "dtype", "shape", "strides", "offset", "_win", "_size")
 
     def __init__(self, buffer: DeviceBuffer, dtype, shape, strides=None, offset: int = 0) -> None:
-        self.buffer = buffer
+        # `buffer` is bound LAST, together with the user count: a constructor that raises half-way
+        # must not leave a Store whose __del__ un-counts a user it never counted (fusion.py treats
+        # an output with zero users as unobservable)
         self.dtype = np.dtype(dtype)
         self.shape = tuple(int(s) for s in shape)
         self.strides = (c_strides(self.shape, self.dtype.itemsize) if strides is None
@@ -35,14 +37,17 @@ class Store:
         self.offset = int(offset)
         self._win = None    # fusion._Window of this (immutable) store, built on first capture
         self._size = None
+        self.buffer = buffer
         if buffer is not None:  # (shape-only probes carry no buffer)
             buffer.users += 1
 
     def __del__(self) -> None:
         try:
-            self.buffer.users -= 1
-        except Exception:
-            pass
+            buffer = self.buffer  # AttributeError if __init__ never got that far
+        except AttributeError:
+            return
+        if buffer is not None:
+            buffer.users -= 1
 
     # ------------------------------------------------------------------ construction
     @staticmethod

@@ -17,5 +17,6 @@ from .module import *  # noqa: F401,F403
 from .module import all, any, max, min, sum  # noqa: F401,A004
 from ._ufunc.math import abs  # noqa: F401,A004
 from .runtime import runtime  # noqa: F401
+from .distributed import replicated  # noqa: F401
 
 __version__ = "0.1.0"

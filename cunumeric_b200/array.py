@@ -146,6 +146,14 @@ class ndarray:
             raise NotImplementedError("asynchronous to_host of a partitioned array")
         return self._thunk.to_host_async(out)
 
+    def to_host_rows(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Counterpart of from_host_rows: THIS rank's block of rows (the whole array on one GPU),
+        copied into `out` (e.g. pinned) without any inter-GPU traffic."""
+        local = getattr(self._thunk, "local_block_to_host", None)
+        if local is not None:
+            return local(out)
+        return self._thunk.__numpy_array__(out)
+
     def item(self, *args):
         return self.__array__().item(*args)
 

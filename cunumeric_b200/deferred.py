@@ -211,7 +211,7 @@ class DeferredArray:
         assert out.flags.c_contiguous and out.shape == tuple(self.shape) and out.dtype == self.dtype
         if src.base.buffer.ready_event is not None:
             runtime.wait_ready(src.base.buffer)
-        return HostFuture(runtime.copy_d2h_async(out, src.base.ptr), src, out)
+        return HostFuture(runtime.copy_d2h_async(out, src.base.ptr, src.base.buffer), src, out)
 
     def __numpy_array__(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Blocking device->host read (the reference blocks in get_scalar_array / inline mapping)."""

@@ -21,7 +21,7 @@ from typing import Any, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import _lib
+from . import _lib, fusion
 from .config import BinaryOpCode, ConvertCode, UnaryOpCode, UnaryRedCode, dtype_code
 from .deferred import (_ARG_REDS, _UNARY_RED_IDENTITIES, DeferredArray, _basic_index,
                        launch_scalar_red)
@@ -105,6 +105,28 @@ class PartitionedArray:
             runtime.copy_h2d(out.local_rows(lo, hi).base.ptr, src)
         return out
 
+    @staticmethod
+    def from_local_rows(block: np.ndarray, global_rows: int,
+                        halo: int = DEFAULT_HALO) -> "PartitionedArray":
+        """SPMD upload: `block` holds THIS rank's rows of a (global_rows, ...) array split evenly
+        over the ranks (RowPartition.even) — no rank ever materialises the whole array."""
+        block = np.ascontiguousarray(block)
+        out = PartitionedArray.empty((int(global_rows),) + block.shape[1:], block.dtype, halo=halo)
+        lo, hi = out.part.bounds(runtime.rank)
+        if block.shape[0] != hi - lo:
+            raise ValueError(f"rank {runtime.rank} owns rows [{lo}, {hi}) of {global_rows}: expected "
+                             f"a block of {hi - lo} rows, got {block.shape[0]}")
+        if hi > lo:
+            runtime.copy_h2d(out.local_rows(lo, hi).base.ptr, block)
+        return out
+
+    def local_block_to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """This rank's rows of the view, copied to the host (no communication)."""
+        vlo, vhi = self.owned
+        if vhi > vlo:
+            return self.local_rows(vlo, vhi).__numpy_array__(out)
+        return np.empty((0,) + self.shape[1:], self.dtype) if out is None else out
+
     # ------------------------------------------------------------------ properties
     @property
     def part(self) -> RowPartition:
@@ -180,7 +202,13 @@ class PartitionedArray:
             m.ghost_valid = True
             return
         lo, _ = m.part.bounds(runtime.rank)
-        self._run_transfers(plan_halo(m.part, m.halo), lo - m.halo, m.local)
+        plan = plan_halo(m.part, m.halo)
+        # The exchange keeps its place in program order between the deferred fused chains
+        # (fusion.enqueue): it reads the rows the previous chain writes and fills the ghosts the
+        # next chain reads, and takes its pointers when it runs — the base buffer may have been
+        # renamed by then.  Flushing here instead would launch the previous iteration's chain
+        # before its temporaries have died.
+        fusion.enqueue(lambda: self._run_transfers(plan, lo - m.halo, m.local))
         m.ghost_valid = True
 
     def _ensure_rows(self, needs: Sequence[Tuple[int, int]]) -> None:
@@ -609,6 +637,23 @@ def _min_partition_volume() -> int:
     return int(os.environ.get("CUNUMERIC_B200_MIN_PARTITION", "65536"))
 
 
+_partitioning = [True]
+
+
+class replicated:
+    """`with cunumeric_b200.replicated(): ...` — inside the block new arrays are NOT row-partitioned
+    even in a multi-GPU job: every rank works on its own full copy (independent replicas of a
+    workload that has no exchange step)."""
+
+    def __enter__(self):
+        self._old = _partitioning[0]
+        _partitioning[0] = False
+        return self
+
+    def __exit__(self, *exc) -> None:
+        _partitioning[0] = self._old
+
+
 def create_empty_thunk(shape, dtype, inputs=None) -> Any:
     """runtime.create_empty_thunk (cunumeric/runtime.py:448-460): pick the thunk type for a new
     array.  Single-GPU: always a DeferredArray.  Multi-GPU: row-partitioned when it can be aligned
@@ -618,6 +663,10 @@ def create_empty_thunk(shape, dtype, inputs=None) -> Any:
     if runtime.world_size == 1 or len(shape) == 0:
         return DeferredArray(Store.empty(shape, dtype))
     like = None
+    if not _partitioning[0]:
+        inputs = [i for i in inputs or () if isinstance(getattr(i, "_thunk", None), PartitionedArray)]
+        if not inputs:
+            return DeferredArray(Store.empty(shape, dtype))
     any_partitioned = False
     for inp in inputs or ():
         thunk = getattr(inp, "_thunk", None)
@@ -636,7 +685,7 @@ def create_empty_thunk(shape, dtype, inputs=None) -> Any:
 
 def thunk_from_numpy(array: np.ndarray) -> Any:
     array = np.asarray(array)
-    if runtime.world_size > 1 and array.ndim >= 1 and array.shape[0] >= 2 * runtime.world_size \
+    if runtime.world_size > 1 and _partitioning[0] and array.ndim >= 1 and array.shape[0] >= 2 * runtime.world_size \
             and array.size >= _min_partition_volume():
         return PartitionedArray.from_numpy(array)
     return DeferredArray.from_numpy(array)

@@ -119,17 +119,38 @@ class _Chain:
         # looks at windows of the same allocation (usually none)
         self.w_by_buf: dict = {}
         self.r_by_buf: dict = {}
+        # id(buffer) -> (window, offset, rows, row_bytes, pitch): writes to this buffer are redirected
+        # to a fresh block (WAR renaming, see capture())
+        self.renamed: dict = {}
+
+
+class _Opaque:
+    """A non-elementwise step (e.g. the NCCL halo exchange) that must keep its place in program
+    order between deferred chains.  `fn()` obtains its pointers when it RUNS."""
+
+    __slots__ = ("fn",)
+
+    def __init__(self, fn) -> None:
+        self.fn = fn
 
 
 _PLAIN_DTYPES = frozenset(np.dtype(t) for t in (
     np.bool_, np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64,
     np.float16, np.float32, np.float64, np.complex64, np.complex128))
 _chain = _Chain()
+# Sealed chains / opaque steps that have not run yet, oldest first.  A chain is not launched the
+# moment a hazard closes it: it waits here until `_MAX_SEALED` younger chains have been sealed (or
+# anything needs device memory).  By then the Python temporaries it produced have usually been
+# dropped (`average`, `work` of the previous Jacobi iteration), so their stores are elided — the
+# liveness test runs at launch time, not at capture time.
+_queue: list = []
+_MAX_SEALED = max(0, int(os.environ.get("CUNUMERIC_B200_FUSION_DEPTH", "1")))
+_RENAME = os.environ.get("CUNUMERIC_B200_RENAME", "1").lower() not in ("0", "off", "false")
 _flushing = False
 _seen: dict = {}
 _kernels: dict = {}   # signature hash -> (vec kernel, strided kernel, plan class) | None (= unusable)
 stats = {"captured": 0, "fused_launches": 0, "fused_tasks": 0, "replayed_tasks": 0,
-         "elided_tasks": 0, "compiled": 0}
+         "elided_tasks": 0, "compiled": 0, "renamed": 0, "deferred": 0}
 
 
 _rt: list = []
@@ -143,7 +164,7 @@ def _get_runtime():
 
 
 def pending() -> bool:
-    return bool(_chain.tasks) and not _flushing
+    return (bool(_chain.tasks) or bool(_queue)) and not _flushing
 
 
 # ---------------------------------------------------------------------------------------------
@@ -172,7 +193,7 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
     c = _chain
     if c.tasks and (c.shape != shape or len(c.tasks) >= MAX_TASKS or
                     len(c.ext_index) + len(rhs) > MAX_INPUTS):
-        flush()
+        seal()
         c = _chain
     out_w = lhs._win
     if out_w is None:
@@ -183,26 +204,40 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
         if w is None:
             w = r._win = _Window(r)
         in_w.append(w)
+    rename = None
     if c.tasks:
-        hazard = False
+        hazard = war = False
         written = c.written
         for w in in_w:  # read of something the chain writes through a different window
             if w.key not in written:
                 for ww in c.w_by_buf.get(id(w.buffer), ()):
                     if w.lo < ww.hi and ww.lo < w.hi:
                         hazard = True
+        bid = id(out_w.buffer)
+        if not hazard and out_w.key not in written:
+            if bid in c.renamed:  # a second write window on a renamed buffer: keep it simple
+                hazard = True
+            for ww in c.w_by_buf.get(bid, ()):  # write over a chain output, different window
+                if out_w.lo < ww.hi and ww.lo < out_w.hi:
+                    hazard = True
         if not hazard:
-            bid = id(out_w.buffer)
-            if out_w.key not in written:
-                for ww in c.w_by_buf.get(bid, ()):  # write over a chain output, different window
-                    if out_w.lo < ww.hi and ww.lo < out_w.hi:
-                        hazard = True
             for rw in c.r_by_buf.get(bid, ()):  # write over something read through another window
                 if rw.key != out_w.key and out_w.lo < rw.hi and rw.lo < out_w.hi:
+                    war = True
+            if war and bid not in c.renamed:
+                # Write-after-read against the chain's own (shifted) operands — the stencil's
+                # `center[:] = work` after reading north/east/west/south of the same grid.  Instead
+                # of closing the chain, redirect the write to a FRESH block for the whole buffer
+                # (register renaming at buffer granularity): the chain keeps reading the old block,
+                # the bytes outside the written window are copied over (cnb_copy_complement), and
+                # the buffer object switches to the new block once the kernel is queued.
+                rename = _rename_geometry(c, out_w) if _RENAME else None
+                if rename is None:
                     hazard = True
         if hazard:
-            flush()
+            seal()
             c = _chain
+            rename = None
     c.shape = shape
     ins = []
     for w in in_w:
@@ -217,6 +252,9 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
             c.ext.append(w)
             c.ext_index[w.key] = vid
             c.r_by_buf.setdefault(id(w.buffer), []).append(w)
+            # a chain that has not run yet reads this buffer: an OLDER pending chain must not
+            # elide the store that produces it, even if every Store onto it has died meanwhile
+            w.buffer.readers += 1
         ins.append(vid)
     # an input window of THIS task that overlaps its own output through a different window is
     # resolved by the caller (DeferredArray._copy_if_overlapping) before we get here
@@ -225,6 +263,8 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
     c.ext.append(None)
     if out_w.key not in c.written:
         c.w_by_buf.setdefault(id(out_w.buffer), []).append(out_w)
+    if rename is not None:
+        c.renamed[id(out_w.buffer)] = rename
     c.written[out_w.key] = (out, out_w)
     c.tasks.append(_Task(kind, int(op), int(nan_op), tuple(ins), out, out_w))
     stats["captured"] += 1
@@ -234,17 +274,91 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
 # ---------------------------------------------------------------------------------------------
 # flush
 # ---------------------------------------------------------------------------------------------
-def flush() -> None:
-    """Run the open chain (fused if possible, else op-by-op) and start a new one."""
-    global _chain, _flushing
+def seal() -> None:
+    """Close the open chain.  It runs once `_MAX_SEALED` younger chains are sealed behind it, or at
+    the next flush()."""
+    global _chain
     if _flushing or not _chain.tasks:
         return
-    c, _chain = _chain, _Chain()
+    _queue.append(_chain)
+    _chain = _Chain()
+    stats["deferred"] += 1
+    _drain(_MAX_SEALED)
+
+
+def enqueue(fn) -> None:
+    """Run `fn()` in program order with respect to the deferred chains: right away if nothing is
+    pending, else after everything captured so far (and before everything captured later)."""
+    if _flushing or not pending():
+        fn()
+        return
+    seal()
+    if not _queue:
+        fn()
+        return
+    _queue.append(_Opaque(fn))
+
+
+def flush() -> None:
+    """Run everything that is pending (fused if possible, else op-by-op), in program order."""
+    global _chain
+    if _flushing:
+        return
+    if _chain.tasks:
+        _queue.append(_chain)
+        _chain = _Chain()
+    if _queue:
+        _drain(0)
+
+
+def _drain(keep: int) -> None:
+    """Run the oldest pending steps until at most `keep` sealed chains remain."""
+    global _flushing
+    if _flushing:
+        return
     _flushing = True
     try:
-        _run_chain(c)
+        while _queue:
+            if sum(1 for q in _queue if isinstance(q, _Chain)) <= keep and \
+                    not isinstance(_queue[0], _Opaque):
+                break
+            step = _queue.pop(0)
+            if isinstance(step, _Opaque):
+                step.fn()
+            else:
+                _run_chain(step)
     finally:
         _flushing = False
+
+
+def _rename_geometry(c: _Chain, w: _Window):
+    """(window, offset, rows, row_bytes, pitch) if `w` is a pitched box (inner-contiguous rows, positive
+    strides) that covers at least half of its buffer and is the chain's first write to it — the
+    cases where copying the complement costs less than the write itself.  Else None."""
+    buf = w.buffer
+    if id(buf) in c.w_by_buf or buf.shared:
+        return None
+    item = w.dtype.itemsize
+    dims = sorted(((st, n) for n, st in zip(w.shape, w.strides) if n != 1), reverse=True)
+    if any(st <= 0 for st, _ in dims):
+        return None
+    # merge jointly contiguous dims, innermost first
+    row_bytes, rest = item, []
+    for st, n in reversed(dims):
+        if not rest and st == row_bytes:
+            row_bytes *= n
+        else:
+            rest.append((st, n))
+    if len(rest) > 1:
+        return None
+    pitch, rows = rest[0] if rest else (row_bytes, 1)
+    if rows > 1 and pitch < row_bytes:
+        return None
+    if 2 * rows * row_bytes < buf.nbytes:
+        return None
+    if w.offset + (rows - 1) * pitch + row_bytes > buf.nbytes:
+        return None
+    return (w, w.offset, rows, row_bytes, pitch)
 
 
 _plan_memo: dict = {}   # structural key of a chain -> (entry, n_keep, output value ids, input value ids)
@@ -252,8 +366,15 @@ _plan_memo: dict = {}   # structural key of a chain -> (entry, n_keep, output va
 
 def _run_chain(c: _Chain) -> None:
     runtime = _rt[0] if _rt else _get_runtime()
-    # outputs somebody can still observe: latest write per window, buffer still has a live Store
-    live = [(vid, w) for vid, w in c.written.values() if w.buffer.users > 0]
+    # this chain's own reads are resolved by this launch: what remains in `readers` are the reads
+    # of YOUNGER pending chains
+    for w in c.ext:
+        if w is not None:
+            w.buffer.readers -= 1
+    # outputs somebody can still observe: latest write per window; the buffer still has a live
+    # Store, or a pending chain reads it
+    live = [(vid, w) for vid, w in c.written.values()
+            if w.buffer.users > 0 or w.buffer.readers > 0]
     # A program that repeats (a time-step loop) produces structurally identical chains: value ids
     # are assigned in program order, so (tasks, live outputs, dtypes, scalar flags) identifies the
     # dead-code elimination result, the signature and the kernel without redoing that work.
@@ -267,7 +388,7 @@ def _run_chain(c: _Chain) -> None:
         by_vid = {vid: w for vid, w in live}
         stats["elided_tasks"] += len(c.tasks) - n_keep
         if _launch(entry, c.shape, [by_vid[v] for v in out_vids], [c.ext[v] for v in in_vids],
-                   n_keep):
+                   n_keep, c.renamed):
             return
     needed = set(v for v, _ in live)
     keep: List[_Task] = []
@@ -316,7 +437,7 @@ def _run_chain(c: _Chain) -> None:
     if len(_plan_memo) > 4096:
         _plan_memo.clear()
     _plan_memo[memo_key] = (entry, len(keep), [v for _, v, _ in out_pairs], in_vids)
-    if not _launch(entry, c.shape, out_windows, in_windows, len(keep)):
+    if not _launch(entry, c.shape, out_windows, in_windows, len(keep), c.renamed):
         _replay(c, keep)
 
 
@@ -357,7 +478,7 @@ def _replay(c: _Chain, tasks: List[_Task]) -> None:
 # ---------------------------------------------------------------------------------------------
 # kernel lookup / generation / compilation
 # ---------------------------------------------------------------------------------------------
-_GENERATOR_VERSION = 3
+_GENERATOR_VERSION = 4
 _src_tag: List[str] = []
 
 
@@ -500,18 +621,23 @@ def _geometry(sig):
     e = max(1, min(16 // max_out, 64 // max_in))
     in_bytes = sum(arr_sizes)
     u = max(1, min(8, 128 // max(1, e * in_bytes))) if in_bytes else 4
-    if len(tasks_sig) > 16:
-        u = min(u, 2)
+    # long chains are issue-bound, not memory-bound (Black-Scholes: ~170 instructions per element):
+    # one chunk per thread keeps the register count low enough for 5-6 resident CTAs per SM, which
+    # is what fills the issue slots (measured: 0.616 -> 0.586 ms per 1e8 options, profiles/r02_*)
+    heavy = len(tasks_sig) > 16
+    if heavy:
+        u = 1
     # strided kernel: batches of B elements per thread.  Operands of a fused chain are often shifted
     # views of one array (the stencil's five neighbours), whose loads mostly hit L1/L2 but still
     # occupy the thread's load slots, so keep >= 4 elements (~160 B of requests) in flight
     b = max(4, min(16, 64 // max(1, in_bytes)))
-    b = int(os.environ.get("CNB_FUSED_B", b))           # tuning knobs (part of the cache key)
-    u = int(os.environ.get("CNB_FUSED_U", u))
+    b = int(os.environ.get("CNB_FUSED_B") or b)           # tuning knobs (part of the cache key)
+    u = int(os.environ.get("CNB_FUSED_U") or u)
     while e * u < b:
         u += 1
     return {"E": e, "U": u, "B": b, "TILE": THREADS * e * u, "in_sizes": in_sizes,
-            "out_sizes": out_sizes, "minblocks": int(os.environ.get("CNB_FUSED_MINBLOCKS", "0"))}
+            "out_sizes": out_sizes, "minblocks": int(os.environ.get("CNB_FUSED_MINBLOCKS", "0")),
+            "ctas_per_sm": 6 if heavy else 0}
 
 
 def generate_source(sig, h: str) -> str:
@@ -693,7 +819,72 @@ def _canonical(shape, strides_list):
     return [(n, st) for n, st in merged]
 
 
-def _launch(entry, shape, out_windows, in_windows, ntasks: int) -> bool:
+def _resolve_pointers(out_windows, in_windows, renamed):
+    """Device pointers of the windows of one fused launch, and a `commit()` to call once the
+    kernel is queued.  Inputs (and outputs of buffers that are not renamed) point into the
+    buffers' current blocks.  An output window of a RENAMED buffer points into a fresh block that
+    already holds a copy of everything outside the window; commit() makes the buffer object adopt
+    that block and returns the old one to the allocator (safe in stream order: every later user
+    is queued behind this kernel)."""
+    from .runtime import runtime
+
+    for w in out_windows:
+        if w.buffer.ready_event is not None:
+            runtime.wait_ready(w.buffer)
+    for w in in_windows:
+        if w.buffer.ready_event is not None:
+            runtime.wait_ready(w.buffer)
+    in_ptrs = [w.buffer.ptr + w.offset for w in in_windows]
+    out_ptrs = []
+    swaps = []
+    fresh: dict = {}
+    for w in out_windows:
+        buf = w.buffer
+        geo = renamed.get(id(buf)) if renamed else None
+        if geo is None or geo[0].key != w.key:
+            out_ptrs.append(buf.ptr + w.offset)
+            continue
+        if id(buf) not in fresh:
+            old_ptr = buf.ptr
+            new_base, new_ptr = runtime._take_block(buf.nbytes)
+            _, offset, rows, row_bytes, pitch = geo
+            _lib.check(runtime.lib.cnb_copy_complement(new_ptr, old_ptr, buf.nbytes, offset, rows,
+                                                       row_bytes, pitch, runtime.stream))
+            fresh[id(buf)] = new_ptr
+            swaps.append((buf, new_base, new_ptr))
+            stats["renamed"] += 1
+        out_ptrs.append(fresh[id(buf)] + w.offset)
+
+    def commit() -> None:
+        for buf, new_base, new_ptr in swaps:
+            runtime.adopt_block(buf, new_base, new_ptr)
+
+    return out_ptrs + in_ptrs, commit
+
+
+def _distinct_bytes(windows, dims_of) -> int:
+    """Algorithmic bytes of one fused launch: distinct bytes touched per buffer.  Windows of one
+    buffer whose byte ranges overlap (the five shifted views of the stencil grid) are counted once:
+    min(sum of their sizes, length of the union of their ranges)."""
+    spans: dict = {}
+    total = 0
+    for k, w in enumerate(windows):
+        spans.setdefault(id(w.buffer), []).append((w.lo, w.hi, dims_of(k) * w.dtype.itemsize))
+    for lst in spans.values():
+        lst.sort()
+        cur_lo, cur_hi, cur_n = lst[0]
+        for lo, hi, n in lst[1:]:
+            if lo < cur_hi:
+                cur_hi = max(cur_hi, hi)
+                cur_n = min(cur_n + n, cur_hi - cur_lo)
+            else:
+                total += cur_n
+                cur_lo, cur_hi, cur_n = lo, hi, n
+        total += cur_n
+    return total
+
+
+def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None) -> bool:
     from .runtime import runtime
 
     k_vec, k_str, plan_cls, geo, _ = entry
@@ -706,14 +897,11 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int) -> bool:
     sizes = geo["out_sizes"] + geo["in_sizes"]
     E = geo["E"]
     n_out = len(out_windows)
-    for w in in_windows:
-        if w.buffer.ready_event is not None:
-            runtime.wait_ready(w.buffer)
+    ptrs, commit = _resolve_pointers(out_windows, in_windows, renamed)
     plan = plan_cls()
     vec = True
-    algo = 0
     for k, w in enumerate(windows):
-        ptr = w.buffer.ptr + w.offset
+        ptr = ptrs[k]
         plan.op[k].ptr = ptr
         plan.op[k].inner_stride = inner_st[k]
         plan.op[k].row_stride = row_st[k]
@@ -724,8 +912,8 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int) -> bool:
             vec = False
         if ptr % align or row_st[k] % align:
             vec = False
-        distinct = (inner if inner_st[k] != 0 else 1) * (rows if row_st[k] != 0 else 1)
-        algo += distinct * size
+    algo = _distinct_bytes(
+        windows, lambda k: (inner if inner_st[k] != 0 else 1) * (rows if row_st[k] != 0 else 1))
     tile = geo["TILE"]
     out_pad = 0
     if not vec and inner_st[0] == sizes[0] and sizes[0] < 128:
@@ -736,7 +924,8 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int) -> bool:
     plan.vec, plan.out_pad = int(vec), out_pad
     _lib.check(runtime.lib.cnb_launch_fused(k_vec if vec else k_str, ctypes.byref(plan),
                                             ctypes.sizeof(plan), plan.num_tiles, inner * rows, algo,
-                                            ntasks, runtime.stream))
+                                            ntasks, geo["ctas_per_sm"], runtime.stream))
+    commit()
     stats["fused_launches"] += 1
     stats["fused_tasks"] += ntasks
     return True

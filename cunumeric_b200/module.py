@@ -96,9 +96,26 @@ def from_host(host: np.ndarray, blocking: bool = True) -> ndarray:
     be pinned, see pinned_empty, and must stay untouched until the result is first used) so that it
     overlaps with kernels already queued."""
     host = np.asarray(host)
-    if blocking or host.ndim == 0 or runtime.world_size > 1:
+    from .distributed import _partitioning
+
+    if blocking or host.ndim == 0 or (runtime.world_size > 1 and _partitioning[0]):
         return convert_to_cunumeric_ndarray(host)
     return ndarray(shape=host.shape, dtype=host.dtype, thunk=DeferredArray.from_numpy_async(host))
+
+
+def from_host_rows(block: np.ndarray, global_rows: int) -> ndarray:
+    """SPMD upload of a row-partitioned array: every rank passes ITS block of rows (the even split
+    of `global_rows` over the ranks) — pinned memory is read asynchronously.  With one GPU the block
+    is the whole array."""
+    block = np.asarray(block)
+    if runtime.world_size == 1:
+        if block.shape[0] != int(global_rows):
+            raise ValueError("single-GPU job: the block must hold every row")
+        return convert_to_cunumeric_ndarray(block)
+    from .distributed import PartitionedArray
+
+    thunk = PartitionedArray.from_local_rows(block, global_rows)
+    return ndarray(shape=thunk.shape, dtype=thunk.dtype, thunk=thunk)
 
 
 def map_chunks(fn, inputs, outputs, chunk: int) -> None:

@@ -22,7 +22,8 @@ class DeviceBuffer:
     counting can be handed out again immediately: stream order already serialises the old reader
     and the new writer); misses go to the stream-ordered CUDA pool."""
 
-    __slots__ = ("_ptr", "base", "nbytes", "_runtime", "ready_event", "users", "__weakref__")
+    __slots__ = ("_ptr", "base", "nbytes", "_runtime", "ready_event", "busy_event", "users",
+                 "readers", "shared", "__weakref__")
 
     def __init__(self, runtime: "Runtime", nbytes: int) -> None:
         self._runtime = runtime
@@ -36,6 +37,12 @@ class DeviceBuffer:
         # number of live Store windows onto this buffer (fusion.py: an output nobody can observe
         # any more is not written)
         self.users = 0
+        # number of captured-but-not-yet-launched chains that read this buffer (fusion.py)
+        self.readers = 0
+        # a cached constant shared between arrays (runtime.scalar_buffer): never renamed
+        self.shared = False
+        # completion event of an asynchronous D2H copy that may still be reading the block
+        self.busy_event = None
 
     @property
     def ptr(self) -> int:
@@ -49,6 +56,12 @@ class DeviceBuffer:
         can observe any more."""
         rt = self._runtime
         if rt is not None and rt.lib is not None and self._ptr:
+            # a copy stream may still be writing (H2D) or reading (D2H) the block: its next owner
+            # only ever sees the compute stream, so order that stream behind the copy first
+            for ev in (self.ready_event, self.busy_event):
+                if ev is not None:
+                    rt.lib.cnb_stream_wait_event(rt.stream, ev)
+            self.ready_event = self.busy_event = None
             rt._give_block(self.base, self._ptr, self.nbytes)
         self.base = self._ptr = None
 
@@ -179,6 +192,19 @@ class Runtime:
         self._free_blocks.setdefault(nbytes, []).append((base, ptr))
         self._cached_bytes += nbytes
 
+    def adopt_block(self, buf: DeviceBuffer, new_base: int, new_ptr: int) -> None:
+        """`buf` switches to a fresh block (fusion.py WAR renaming); the old one goes back to the
+        free list.  Everything that will touch either block later is queued on the compute stream
+        behind the kernel that filled the new one; an asynchronous D2H copy still reading the old
+        block (copy stream) is waited for first."""
+        if buf.busy_event is not None:
+            _lib.check(self.lib.cnb_stream_wait_event(self.stream, buf.busy_event))
+            buf.busy_event = None
+        old_base, old_ptr = buf.base, buf._ptr
+        buf.base, buf._ptr = new_base, new_ptr
+        if old_ptr:
+            self._give_block(old_base, old_ptr, buf.nbytes)
+
     def release_cached_memory(self) -> None:
         """Return every cached block to the CUDA pool."""
         for blocks in self._free_blocks.values():
@@ -239,9 +265,10 @@ class Runtime:
             buf.ready_event = None
             self._recycle_event(ev)
 
-    def copy_d2h_async(self, dst: np.ndarray, src_ptr: int):
+    def copy_d2h_async(self, dst: np.ndarray, src_ptr: int, buf: Optional[DeviceBuffer] = None):
         """Start a D2H copy on the D2H stream once the compute stream reaches this point; returns
-        the event that marks its completion."""
+        the event that marks its completion (`buf`: the allocation being read, told to wait for
+        this event before it gives its block up)."""
         assert dst.flags.c_contiguous
         _, d2h = self._copy_streams()
         ev = self._event()
@@ -250,6 +277,8 @@ class Runtime:
         if dst.nbytes:
             _lib.check(self.lib.cnb_memcpy_d2h(dst.ctypes.data, src_ptr, dst.nbytes, d2h))
         _lib.check(self.lib.cnb_event_record(ev, d2h))
+        if buf is not None:
+            buf.busy_event = ev
         return ev
 
     def scalar_buffer(self, value: np.ndarray) -> DeviceBuffer:
@@ -261,6 +290,7 @@ class Runtime:
             if len(self._scalar_cache) > 1024:
                 self._scalar_cache.clear()
             buf = self.allocate(value.nbytes)
+            buf.shared = True
             staged = np.ascontiguousarray(value)
             if not self.dry_run:
                 self.copy_h2d(buf.ptr, staged)

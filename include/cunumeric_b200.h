@@ -260,8 +260,16 @@ const char* cnb_version(void);
 #define CNB_OP_FUSED 1000
 int cnb_module_load(const void* image, size_t bytes, void** module);
 int cnb_module_get_kernel(void* module, const char* name, void** kernel);
+/* max_ctas_per_sm: resident CTAs per SM the persistent grid may use (0 = the memory-bound default, 3) */
 int cnb_launch_fused(void* kernel, const void* plan, size_t plan_bytes, int64_t num_tiles,
-                     int64_t elements, int64_t algorithmic_bytes, int32_t ntasks, void* stream);
+                     int64_t elements, int64_t algorithmic_bytes, int32_t ntasks,
+                     int32_t max_ctas_per_sm, void* stream);
+/* dst <- src over [0, nbytes) EXCEPT the pitched window {offset + r * pitch .. + row_bytes, r < rows}.
+ * Used when a fused chain redirects a write to a fresh copy of its buffer to remove a
+ * write-after-read hazard against its own shifted operands (register renaming at buffer
+ * granularity; the stencil's `center[:] = work`, examples/stencil.py:49). */
+int cnb_copy_complement(void* dst, const void* src, size_t nbytes, int64_t offset, int64_t rows,
+                        int64_t row_bytes, int64_t pitch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU exchange (one process per GPU).  In the reference these steps are implicit Legion

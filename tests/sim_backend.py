@@ -82,6 +82,21 @@ class SimLib:
     def cnb_stream_synchronize(self, stream):
         return 0
 
+    def cnb_stream_wait_event(self, stream, event):
+        return 0
+
+    def cnb_copy_complement(self, dst, src, nbytes, offset, rows, row_bytes, pitch, stream):
+        """dst <- src outside the pitched window (include/cunumeric_b200.h)."""
+        d = np.frombuffer((ctypes.c_uint8 * nbytes).from_address(dst), dtype=np.uint8)
+        s = np.frombuffer((ctypes.c_uint8 * nbytes).from_address(src), dtype=np.uint8)
+        keep = np.ones(nbytes, dtype=bool)
+        for r in range(rows):
+            keep[offset + r * pitch: offset + r * pitch + row_bytes] = False
+        d[keep] = s[keep]
+        self.launches += 1
+        self.complement_copies = getattr(self, "complement_copies", 0) + 1
+        return 0
+
     def cnb_launch_count(self):
         return self.launches
 
@@ -119,8 +134,8 @@ class SimLib:
         return 0
 
 
-def window_view(w):
-    return _window(w.buffer.ptr + w.offset, w.dtype, w.shape, w.strides)
+def window_view(w, ptr=None):
+    return _window(w.buffer.ptr + w.offset if ptr is None else ptr, w.dtype, w.shape, w.strides)
 
 
 def make_fused_launcher(lib: SimLib, schedule_rng=None):
@@ -150,11 +165,16 @@ def make_fused_launcher(lib: SimLib, schedule_rng=None):
                 vals[out] = np.asarray(r, dtype=DTYPES[code])
         return vals
 
-    def launch(entry, shape, out_windows, in_windows, ntasks):
+    def launch(entry, shape, out_windows, in_windows, ntasks, renamed=None):
+        from cunumeric_b200 import fusion
+
         _, sig = entry
         outs = sig[2]
-        ins_v = [window_view(w) for w in in_windows]
-        outs_v = [window_view(w) for w in out_windows]
+        # the product's own pointer resolution (incl. WAR renaming: fresh block + complement copy)
+        ptrs, commit = fusion._resolve_pointers(out_windows, in_windows, renamed)
+        n_out = len(out_windows)
+        outs_v = [window_view(w, p) for w, p in zip(out_windows, ptrs[:n_out])]
+        ins_v = [window_view(w, p) for w, p in zip(in_windows, ptrs[n_out:])]
         mode = int(rng.integers(3)) if len(shape) >= 1 and shape[0] > 1 else 0
         if mode == 0:
             vals = evaluate(sig, {i: v.copy() for i, v in enumerate(ins_v)})
@@ -167,6 +187,8 @@ def make_fused_launcher(lib: SimLib, schedule_rng=None):
                 pairs = list(zip(outs, outs_v))
                 for (v, code), o in (reversed(pairs) if mode == 1 else pairs):
                     o[i:i + 1] = vals[v]
+        commit()
+        lib.stored_outputs = getattr(lib, "stored_outputs", []) + [len(out_windows)]
         lib.launches += 1
         lib.fused_launches += 1
         return True

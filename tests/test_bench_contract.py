@@ -21,23 +21,30 @@ def _oracle_available() -> bool:
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     if not _oracle_available():
         pytest.skip("oracle/_ref not built")
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                          "--steps", "2", "--warmup", "1", "--cpu-sample", "200000"],
-                         capture_output=True, text=True, timeout=300, cwd=ROOT)
-    assert res.returncode == 0, res.stderr[-2000:]
-    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
-    assert len(lines) == 1, lines
-    r = json.loads(lines[0])
-    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
-                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
-                "cpu_baseline", "e2e"):
-        assert key in r, key
-    assert r["impl"] == "reference" and r["metric"] == "black_scholes_elements_per_second"
-    assert r["unit"] == "options/s" and r["higher_is_better"] is True and r["vs_baseline"] is None
-    assert r["value"] > 0 and r["cpu_baseline"]["kind"] == "reference"
-    assert r["cpu_baseline"]["value"] == r["value"] == r["e2e"]["value"]
-    assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in r["config"] and "model" not in r["config"]
+    for extra, metric, unit in (
+            (["--cpu-stencil-n", "200", "--cpu-stencil-iters", "2"], "stencil_points_per_second",
+             "points/s"),
+            (["--workload", "black_scholes", "--cpu-sample", "200000"],
+             "black_scholes_elements_per_second", "options/s")):
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                              "--steps", "3", "--warmup", "1"] + extra,
+                             capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert res.returncode == 0, res.stderr[-2000:]
+        lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+        assert len(lines) == 1, lines
+        r = json.loads(lines[0])
+        for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                    "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                    "cpu_baseline", "e2e"):
+            assert key in r, key
+        assert r["impl"] == "reference" and r["metric"] == metric and r["unit"] == unit
+        assert r["steps"] == 3 and r["warmup"] == 1          # --steps / --warmup are honoured
+        assert r["higher_is_better"] is True and r["vs_baseline"] is None
+        assert r["value"] > 0 and r["cpu_baseline"]["kind"] == "reference"
+        assert r["cpu_baseline"]["value"] == r["value"] == r["e2e"]["value"]
+        assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["d2h_bytes_per_step"] == 0
+        assert "workload" in r["config"] and "model" not in r["config"]
+        assert "sample" in r["config"]["workload"]           # the sampled size is stated there
 
 
 def test_reference_arm_other_ranks_exit_quietly():

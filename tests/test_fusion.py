@@ -67,17 +67,22 @@ def test_trace_and_compile_without_a_device(tmp_path, monkeypatch):
     assert "63 tasks, 16 inputs, 2 stored outputs" in text  # 61 intermediates stay in registers
     assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
 
+    held = []
+
     def stencil():
         # lazily allocated grid: the boundary fills are skipped in a dry run
         g = cn.empty((66, 66), dtype=np.float64)
-        return stencil_run(g, 2)
+        held.append((g, stencil_run(g, 2)))
 
-    # per iteration: [4 ADD + MULTIPLY] fuse; the COPY back into `center` overlaps the shifted
-    # views the chain reads, so it must NOT join the chain
+    # per iteration ONE chain: [4 ADD + MULTIPLY + COPY] — the COPY back into `center` overwrites the
+    # shifted views the chain reads, which write-after-read renaming of the grid buffer makes legal.
+    # Chains are launched one iteration late: iteration 1 stores only the new interior (`average`
+    # and `work` of that iteration are dead by then), the last one also the returned `work`.
     n = fusion.trace_only(stencil)
-    assert n == 1
+    assert n == 2
     texts = [open(tmp_path / f).read() for f in os.listdir(tmp_path) if f.endswith(".cu")]
-    assert any("5 tasks, 6 inputs, 2 stored outputs" in t for t in texts), [t[:120] for t in texts]
+    assert any("6 tasks, 6 inputs, 1 stored outputs" in t for t in texts), [t[:120] for t in texts]
+    assert any("6 tasks, 6 inputs, 2 stored outputs" in t for t in texts), [t[:120] for t in texts]
 
 
 def test_hazard_rules_dry():
@@ -111,6 +116,7 @@ def test_hazard_rules_dry():
         pass  # the fill needs a device; everything before it is what we check
     finally:
         fusion._chain = fusion._Chain()
+        fusion._queue.clear()
         fusion.set_mode(old)
         cn.runtime.dry_run = False
         fusion.drop_scalar_caches()
@@ -126,11 +132,13 @@ def _dry(prog):
     if cn.runtime.lib is not None:
         pytest.skip("runtime already initialised on a device")
     flushed = []
+    _dry.renames = []
     orig = fusion._run_chain
 
     def spy(c):
         live = sum(1 for _, w in c.written.values() if w.buffer.users > 0)
         flushed.append(([t.kind + str(t.op) for t in c.tasks], live))
+        _dry.renames.append((len(c.tasks), live, len(c.renamed)))
         # no compilation in these tests: the chain bookkeeping is what is checked
 
     cn.runtime.dry_run = True
@@ -142,6 +150,7 @@ def _dry(prog):
     finally:
         fusion._run_chain = orig
         fusion._chain = fusion._Chain()
+        fusion._queue.clear()
         fusion.set_mode(old)
         cn.runtime.dry_run = False
         fusion.drop_scalar_caches()
@@ -172,11 +181,14 @@ def test_inplace_update_joins_but_shifted_write_flushes_dry():
         a += b                 # reads and writes the same window: joins
         a *= 2.0               # joins, value of `a` comes from registers
         c = a[1:, :] + 1.0     # a different window of something the chain wrote: flush first
-        a[:-1, :] = c          # writes a window overlapping the chain's read window a[1:, :]: flush
-        return a, c
+        a[:-1, :] = c          # write-after-read on a[1:, :]: joins, `a`'s buffer is RENAMED
+        d = a[:20, :] + 1.0
+        a[10:30, :] = d        # write-after-read again, but the window is < half the buffer: flush
+        return a, c, d
 
     chains = _dry(prog)
-    assert [len(t) for t, _ in chains] == [2, 1, 1]
+    assert [len(t) for t, _ in chains] == [2, 2, 1, 1]
+    assert [r for _, _, r in _dry.renames] == [0, 1, 0, 0]
 
 
 def test_chain_length_and_shape_changes_flush_dry():

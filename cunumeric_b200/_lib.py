@@ -35,6 +35,19 @@ class cnb_trace_record_t(ctypes.Structure):
     ]
 
 
+class cnb_tma_operand_t(ctypes.Structure):
+    _fields_ = [
+        ("base", ctypes.c_void_p),
+        ("width", ctypes.c_int64),
+        ("height", ctypes.c_int64),
+        ("pitch_bytes", ctypes.c_int64),
+        ("elem_bytes", ctypes.c_int32),
+        ("box_width", ctypes.c_int32),
+        ("box_height", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 class CnbError(RuntimeError):
     def __init__(self, code: int, message: str) -> None:
         super().__init__(f"[cunumeric_b200 rc={code}] {message}")
@@ -89,6 +102,8 @@ PROTOTYPES = {
     "cnb_module_get_kernel": (_i32, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cnb_launch_fused": (_i32, [_vp, _vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64,
                                 ctypes.c_int64, _i32, _i32, _vp]),
+    "cnb_launch_fused_tma": (_i32, [_vp, ctypes.POINTER(cnb_tma_operand_t), _i32, _vp, _sz, _i32, _i64,
+                                    _i64, _i64, _i32, _i32, _vp]),
     "cnb_copy_complement": (_i32, [_vp, _vp, _sz, _i64, _i64, _i64, _i64, _vp]),
     "cnb_last_error": (ctypes.c_char_p, []),
     "cnb_version": (ctypes.c_char_p, []),

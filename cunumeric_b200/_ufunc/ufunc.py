@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Any, Dict, Optional, Sequence, Tuple, Union
 
+import math
+
 import numpy as np
 
 from ..config import BinaryOpCode, UnaryOpCode, UnaryRedCode
@@ -119,7 +121,7 @@ class ufunc:
         if len(args) < self.nin or len(args) > max_nargs:
             raise TypeError(f"{self._name}() takes from {self.nin} to {max_nargs} positional "
                             f"arguments but {len(args)} were given")
-        inputs = tuple(convert_to_cunumeric_ndarray(arr) for arr in args[: self.nin])
+        inputs = tuple(convert_to_cunumeric_ndarray(arr, share=True) for arr in args[: self.nin])
         if len(args) > self.nin:
             if out is not None:
                 raise TypeError("cannot specify 'out' as both a positional and keyword argument")
@@ -350,7 +352,10 @@ class binary_ufunc(ufunc):
 
     @classmethod
     def _weak_scalar(cls, value, dtype):
-        key = (dtype.char, type(value), value)
+        # 0.0 == -0.0 (and they hash alike) but `x / -0.0`, `copysign(x, -0.0)`, `x * -0.0` differ:
+        # the sign of a zero is part of the key
+        key = (dtype.char, type(value), value,
+               math.copysign(1.0, value) if value == 0 else 0.0)
         hit = cls._scalar_cache.get(key)
         if hit is None:
             ndarray = _ndarray_type()

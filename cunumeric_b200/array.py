@@ -14,6 +14,7 @@ import numpy as np
 from .config import ConvertCode, UnaryOpCode, UnaryRedCode, is_supported_dtype
 from .deferred import DeferredArray
 from .distributed import create_empty_thunk, thunk_from_numpy
+from .runtime import runtime
 from .store import Store
 
 
@@ -44,9 +45,22 @@ def convert_to_cunumeric_ndarray(obj: Any, share: bool = False) -> "ndarray":
     if host.dtype == object or not is_supported_dtype(host.dtype):
         raise TypeError(f"cunumeric_b200 does not support dtype={host.dtype}")
     if host.ndim == 0:
-        return ndarray(shape=(), dtype=host.dtype,
-                       thunk=DeferredArray(Store.from_scalar(host), host_scalar=host))
+        if share:
+            # internal, read-only operand (a scalar next to an array in a ufunc call): a window onto
+            # the value-keyed constant cache (runtime.scalar_buffer), with its host value attached
+            return ndarray(shape=(), dtype=host.dtype,
+                           thunk=DeferredArray(Store.from_scalar(host), host_scalar=host))
+        # a user-visible 0-d array owns its buffer: writing to it (`x += 1`, fill, out=x) must never
+        # reach the shared constants, and it carries no host copy that could go stale
+        store = Store.empty((), host.dtype)
+        if not runtime.dry_run:
+            runtime.copy_h2d(store.ptr, np.ascontiguousarray(host))
+        return ndarray(shape=(), dtype=host.dtype, thunk=DeferredArray(store))
     return ndarray(shape=host.shape, dtype=host.dtype, thunk=thunk_from_numpy(host))
+
+
+def _rebuild_from_host(host: np.ndarray) -> "ndarray":
+    return convert_to_cunumeric_ndarray(host)
 
 
 def broadcast_where(where, shape):
@@ -193,7 +207,7 @@ class ndarray:
 
     def __setitem__(self, key: Any, value: Any) -> None:
         """array.py:1668-1680 -> deferred.set_item: `view[:] = value` is a UNARY_OP(COPY)."""
-        value = convert_to_cunumeric_ndarray(value)
+        value = convert_to_cunumeric_ndarray(value, share=True)
         if value.dtype != self.dtype:
             value = value._astype(self.dtype, temporary=True)
         view = self._thunk.get_item(key)
@@ -244,6 +258,14 @@ class ndarray:
 
     __copy__ = copy
 
+    def __deepcopy__(self, memo=None) -> "ndarray":
+        """array.py:905 — a deep copy is a device copy (never a walk through Store / DeviceBuffer)."""
+        return self.copy()
+
+    def __reduce__(self):
+        """array.py:1513 — pickling goes through the host array."""
+        return (_rebuild_from_host, (self.__array__(),))
+
     def fill(self, value: Any) -> None:
         self._thunk.fill(np.asarray(value).astype(self.dtype))
 
@@ -271,7 +293,7 @@ class ndarray:
             return self
         if self._thunk.host_scalar is not None:
             with np.errstate(all="ignore"):
-                return convert_to_cunumeric_ndarray(self._thunk.host_scalar.astype(dtype))
+                return convert_to_cunumeric_ndarray(self._thunk.host_scalar.astype(dtype), share=True)
         result = ndarray(self.shape, dtype=dtype, inputs=(self,))
         result._thunk.convert(self._thunk, warn=False, temporary=temporary)
         return result

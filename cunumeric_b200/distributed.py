@@ -517,13 +517,45 @@ def _nccl_allreduce(buf: DeferredArray, red: UnaryRedCode) -> None:
                                               dtype_code(buf.dtype), int(red), runtime.stream))
 
 
+def _needs_gather_fold(dtype: np.dtype, red: UnaryRedCode) -> bool:
+    """Partials NCCL cannot combine the way the local kernels do: 16-bit integers (no NCCL type),
+    complex PROD / MAX / MIN (NCCL only sums pairs of floats), and floating MAX / MIN — ncclMax /
+    ncclMin propagate NaN differently from the reference's fold `if (b > a) a = b`, which would make
+    the result depend on the number of ranks."""
+    if dtype in (np.dtype(np.int16), np.dtype(np.uint16)):
+        return True
+    if dtype.kind == "c" and red != UnaryRedCode.SUM:
+        return True
+    return dtype.kind == "f" and red in (UnaryRedCode.MAX, UnaryRedCode.MIN)
+
+
+def _gather_fold(partial: DeferredArray, red: UnaryRedCode) -> DeferredArray:
+    """ncclAllGather of the per-rank partials, then the library's own reduction kernel along the
+    rank axis (in rank order): the same fold, hence the same NaN behaviour, as on one GPU."""
+    assert partial.base.is_c_contiguous
+    world = runtime.world_size
+    gathered = DeferredArray(Store.empty((world,) + tuple(partial.shape), partial.dtype))
+    _lib.check(runtime.lib.cnb_comm_allgather(runtime.comm, partial.base.ptr, gathered.base.ptr,
+                                              partial.size * partial.dtype.itemsize, runtime.stream))
+    out = DeferredArray(Store.empty(partial.shape, partial.dtype))
+    if partial.size == 1:
+        flat = DeferredArray(gathered.base.reshape_contiguous((world,)))
+        out.unary_reduction(red, flat, None, None, (0,), False, (), None)
+    else:
+        out.unary_reduction(red, gathered, None, 0, (0,), False, (), None)
+    return out
+
+
 def _allreduce(partial: DeferredArray, op: UnaryRedCode, argred: bool, elem: np.dtype
                ) -> DeferredArray:
     """Combine the per-rank partials (dense VAL array, same shape on every rank)."""
     if runtime.world_size == 1:
         return partial
     if not argred:
-        _nccl_allreduce(partial, _COMBINE[op])
+        red = _COMBINE[op]
+        if _needs_gather_fold(partial.dtype, red):
+            return _gather_fold(partial, red)
+        _nccl_allreduce(partial, red)
         return partial
     # arg-reductions: best value across ranks, then the LOWEST index among the ranks that hold it
     is_max = op in (UnaryRedCode.ARGMAX, UnaryRedCode.NANARGMAX)
@@ -531,7 +563,11 @@ def _allreduce(partial: DeferredArray, op: UnaryRedCode, argred: bool, elem: np.
     vals.copy(_field_view(partial, "arg_value"), deep=True)
     best = DeferredArray(Store.empty(partial.shape, elem))
     best.copy(vals, deep=True)
-    _nccl_allreduce(best, UnaryRedCode.MAX if is_max else UnaryRedCode.MIN)
+    red = UnaryRedCode.MAX if is_max else UnaryRedCode.MIN
+    if _needs_gather_fold(best.dtype, red):
+        best = _gather_fold(best, red)
+    else:
+        _nccl_allreduce(best, red)
     args = DeferredArray(Store.empty(partial.shape, np.int64))
     args.copy(_field_view(partial, "arg"), deep=True)
     hit = DeferredArray(Store.empty(partial.shape, np.bool_))

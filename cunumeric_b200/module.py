@@ -206,8 +206,8 @@ def where(a, x=None, y=None) -> ndarray:
                                   "hot-path scope (SURVEY §2.1 row 24)")
     mask = convert_to_cunumeric_ndarray(a)
     xs, ys = x, y
-    x = convert_to_cunumeric_ndarray(x)
-    y = convert_to_cunumeric_ndarray(y)
+    x = convert_to_cunumeric_ndarray(x, share=True)
+    y = convert_to_cunumeric_ndarray(y, share=True)
     # Python scalars are weak, exactly like numpy.where
     common = np.result_type(xs if _is_weak_scalar(xs) else x.dtype,
                             ys if _is_weak_scalar(ys) else y.dtype)

@@ -49,6 +49,18 @@ class Store:
         if buffer is not None:
             buffer.users -= 1
 
+    # A Store counts as a user of its buffer (fusion.py drops stores into buffers nobody observes):
+    # every duplicate has to go through the constructor, and a Store is never pickled (ndarray
+    # pickles through the host array).
+    def __copy__(self) -> "Store":
+        return Store(self.buffer, self.dtype, self.shape, self.strides, self.offset)
+
+    def __deepcopy__(self, memo=None) -> "Store":
+        raise TypeError("a Store is a window onto device memory: copy the ndarray instead")
+
+    def __reduce__(self):
+        raise TypeError("a Store is a window onto device memory: pickle the ndarray instead")
+
     # ------------------------------------------------------------------ construction
     @staticmethod
     def empty(shape, dtype) -> "Store":

@@ -264,6 +264,26 @@ int cnb_module_get_kernel(void* module, const char* name, void** kernel);
 int cnb_launch_fused(void* kernel, const void* plan, size_t plan_bytes, int64_t num_tiles,
                      int64_t elements, int64_t algorithmic_bytes, int32_t ntasks,
                      int32_t max_ctas_per_sm, void* stream);
+/* TMA-staged flavour of a fused chain (north_star: "TMA-staged tiles for strided and transposed"
+ * operands; replaces the per-element div/mod walk of the reference's generic kernels,
+ * binary/binary_op.cu:33-52, pitches.h:46-55, for pitched 2-D views).  Every pitched operand buffer
+ * is described by one tensor map {base, width x height elements, row pitch, box}; the library
+ * encodes them (cuTensorMapEncodeTiled) in front of the generator's parameter tail.  The kernel
+ * stages (rows + halo) x (cols + halo) boxes in shared memory with cp.async.bulk.tensor.2d. */
+typedef struct cnb_tma_operand {
+  void* base;            /* 16-byte aligned start of the buffer */
+  int64_t width;         /* elements per buffer row (row pitch / element size) */
+  int64_t height;        /* whole rows inside the allocation */
+  int64_t pitch_bytes;   /* multiple of 16 */
+  int32_t elem_bytes;    /* 1, 2, 4 or 8 */
+  int32_t box_width;     /* <= 256 elements, box_width * elem_bytes multiple of 16 */
+  int32_t box_height;    /* <= 256 */
+  int32_t reserved;
+} cnb_tma_operand_t;
+int cnb_launch_fused_tma(void* kernel, const cnb_tma_operand_t* ops, int32_t nmaps, const void* tail,
+                         size_t tail_bytes, int32_t smem_bytes, int64_t num_tiles, int64_t elements,
+                         int64_t algorithmic_bytes, int32_t ntasks, int32_t max_ctas_per_sm,
+                         void* stream);
 /* dst <- src over [0, nbytes) EXCEPT the pitched window {offset + r * pitch .. + row_bytes, r < rows}.
  * Used when a fused chain redirects a write to a fresh copy of its buffer to remove a
  * write-after-read hazard against its own shifted operands (register renaming at buffer

@@ -270,3 +270,52 @@ def test_stencil_config_c1_matches_the_reference_arithmetic(mode):
     g_np = stencil_init(1000, np.float64, xp=np)
     w_np = stencil_run(g_np, 100)
     assert np.array_equal(got_w, w_np) and np.array_equal(got_g, g_np)
+
+
+# ------------------------------------------------------------------ advisor findings (round 1)
+@pytest.mark.gpu
+def test_user_zero_d_arrays_do_not_alias_the_constant_cache():
+    """array.py `convert_to_cunumeric_ndarray`: a user-visible 0-d array owns its buffer; in-place
+    writes to it must not change the cached constants later `arr * 2.0` operations read."""
+    x = cn.array(2.0)
+    x += 1
+    assert float(x) == 3.0
+    assert (np.array(cn.ones(4) * 2.0) == 2).all()
+    acc = cn.array(0.0)
+    acc += cn.ones(8).sum()
+    assert float(acc) == 8.0
+    assert (np.array(cn.ones(4) + 0.0) == 1).all()
+    y = cn.asarray(np.float64(5.0))
+    y.fill(7.0)
+    assert float(y) == 7.0 and float(y.astype(np.float32)) == 7.0
+    assert (np.array(cn.ones(3) * 5.0) == 5).all()
+    cn.add(cn.ones(()), 1.0, out=x)
+    assert float(x) == 2.0 and (np.array(cn.full(3, 4.0) / 2.0) == 2).all()
+
+
+@pytest.mark.gpu
+def test_negative_zero_scalar_is_not_confused_with_positive_zero():
+    a = cn.array(np.array([1.0, -2.0, 3.0], dtype=np.float32))
+    assert np.array_equal(np.array(a + 0.0), np.array([1.0, -2.0, 3.0], dtype=np.float32))
+    with np.errstate(divide="ignore"):
+        got = np.array(a / -0.0)
+        exp = np.array([1.0, -2.0, 3.0], dtype=np.float32) / np.float32(-0.0)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(np.signbit(np.array(a * -0.0)), [True, False, True])
+    assert np.array_equal(np.signbit(np.array(a * 0.0)), [False, True, False])
+
+
+@pytest.mark.gpu
+def test_deepcopy_and_pickle_go_through_device_copy_and_host_array():
+    import copy
+    import pickle
+
+    a = cn.array(np.arange(12.0).reshape(3, 4))
+    b = copy.deepcopy(a)
+    b += 1
+    assert np.array_equal(np.array(a), np.arange(12.0).reshape(3, 4))
+    assert np.array_equal(np.array(b), np.arange(12.0).reshape(3, 4) + 1)
+    c = pickle.loads(pickle.dumps(a))
+    assert np.array_equal(np.array(c), np.array(a))
+    with pytest.raises(TypeError):
+        copy.deepcopy(a._thunk.base)

@@ -78,11 +78,16 @@ def test_trace_and_compile_without_a_device(tmp_path, monkeypatch):
     # shifted views the chain reads, which write-after-read renaming of the grid buffer makes legal.
     # Chains are launched one iteration late: iteration 1 stores only the new interior (`average`
     # and `work` of that iteration are dead by then), the last one also the returned `work`.
+    # Each of the two chains is compiled in two flavours: vector / strided, and TMA-staged tiles (the
+    # five shifted views are ONE tensor-map group: one box with a halo serves them all).
     n = fusion.trace_only(stencil)
-    assert n == 2
+    assert n == 4
     texts = [open(tmp_path / f).read() for f in os.listdir(tmp_path) if f.endswith(".cu")]
     assert any("6 tasks, 6 inputs, 1 stored outputs" in t for t in texts), [t[:120] for t in texts]
     assert any("6 tasks, 6 inputs, 2 stored outputs" in t for t in texts), [t[:120] for t in texts]
+    tma = [t for t in texts if "(TMA flavour)" in t]
+    assert len(tma) == 2 and all("6 inputs in 1 tensor-map group(s)" in t for t in tma)
+    assert all("tma_load_2d(" in t and "g0_1_1" in t for t in tma)
 
 
 def test_hazard_rules_dry():
@@ -244,6 +249,58 @@ def test_stencil_fused_is_bit_identical(n, dt):
     assert np.array_equal(fused[0], g_np) and np.array_equal(fused[1], w_np)
     # 4 iterations x [4 ADD + MULTIPLY]; the boundary writes of stencil_init may add one chain
     assert delta["fused_launches"] in (4, 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dt", [(254, np.float64), (1002, np.float64), (254, np.float32),
+                                  (510, np.float32), (126, np.float16)])
+def test_stencil_tma_flavour_is_bit_identical(n, dt):
+    """Even N: the row pitch is a multiple of 16 bytes, so the chain runs as TMA-staged tiles (one box
+    with a halo per tile for the five shifted views, results stored straight from registers)."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200.workloads import stencil_init, stencil_run
+
+    def prog():
+        g = stencil_init(n, dt, xp=cn)
+        w = stencil_run(g, 5)
+        return g, w
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    g_np = stencil_init(n, dt, xp=np)
+    w_np = stencil_run(g_np, 5)
+    if dt != np.float16:
+        assert np.array_equal(fused[0], g_np) and np.array_equal(fused[1], w_np)
+    assert delta["tma_launches"] == 5 and delta["renamed"] == 5
+
+
+@pytest.mark.gpu
+def test_tma_flavour_mixed_groups_and_outputs():
+    """Two buffers (two tensor-map groups, one of them with shifted members), a dense third operand,
+    scalars, a compare + where + convert in the chain, two stored outputs of different dtypes."""
+    import cunumeric_b200 as cn
+
+    rng = pu.rng_for("fusion-tma")
+    a0 = rng.normal(size=(300, 520))
+    b0 = rng.normal(size=(302, 524)).astype(np.float32)
+    c0 = rng.normal(size=(298, 516))
+
+    def prog():
+        a, b, c = cn.array(a0), cn.array(b0), cn.array(c0)
+        up, down = a[0:-2, 3:-1], a[2:, 1:-3]           # one group: shifts (0,3) and (2,1)
+        bb = b[3:-1, 5:-3]                              # fp32 window, 4-byte misaligned
+        t = (up + down) * 0.5 - c
+        m = t > bb.astype(np.float64)
+        r = cn.where(m, t, c * 2.0)
+        q = r.astype(np.float32) + bb
+        return r, q
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    assert delta["tma_launches"] >= 1
+    exp_t = (a0[0:-2, 3:-1] + a0[2:, 1:-3]) * 0.5 - c0
+    exp_r = np.where(exp_t > b0[3:-1, 5:-3].astype(np.float64), exp_t, c0 * 2.0)
+    assert np.array_equal(fused[0], exp_r)
 
 
 @pytest.mark.gpu

@@ -275,6 +275,8 @@ def test_stencil_config_c1_matches_the_reference_arithmetic(mode):
 # ------------------------------------------------------------------ advisor findings (round 1)
 @pytest.mark.gpu
 def test_user_zero_d_arrays_do_not_alias_the_constant_cache():
+    import cunumeric_b200 as cn
+
     """array.py `convert_to_cunumeric_ndarray`: a user-visible 0-d array owns its buffer; in-place
     writes to it must not change the cached constants later `arr * 2.0` operations read."""
     x = cn.array(2.0)
@@ -295,6 +297,8 @@ def test_user_zero_d_arrays_do_not_alias_the_constant_cache():
 
 @pytest.mark.gpu
 def test_negative_zero_scalar_is_not_confused_with_positive_zero():
+    import cunumeric_b200 as cn
+
     a = cn.array(np.array([1.0, -2.0, 3.0], dtype=np.float32))
     assert np.array_equal(np.array(a + 0.0), np.array([1.0, -2.0, 3.0], dtype=np.float32))
     with np.errstate(divide="ignore"):
@@ -307,6 +311,8 @@ def test_negative_zero_scalar_is_not_confused_with_positive_zero():
 
 @pytest.mark.gpu
 def test_deepcopy_and_pickle_go_through_device_copy_and_host_array():
+    import cunumeric_b200 as cn
+
     import copy
     import pickle
 

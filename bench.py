@@ -465,6 +465,15 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
     peak_gbs, peak_src = load_peaks()
     fused_on = args.fusion == "on" and fusion.enabled()
     fusion.set_mode("1" if fused_on else "0")
+    # parity guard on the very path that is about to be timed (partitioned, fused, renamed, TMA):
+    # a small even-N grid, a few iterations, bit-exact against NumPy on every rank
+    ns = 1022
+    small = stencil_init(ns, np.float64)
+    stencil_run(small, 7)
+    ref_small = stencil_init(ns, np.float64, xp=np)
+    stencil_run(ref_small, 7)
+    selfcheck = bool(np.array_equal(np.asarray(small), ref_small))
+    del small
     grid = stencil_init(n, np.float64)
     for _ in range(warmup):
         stencil_run(grid, iters)
@@ -520,6 +529,7 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
                                   "(grouped, stream-ordered)" if world > 1 else "none (1 GPU)"),
                    "halo_bytes_per_iter_per_gpu": {"sent": sent, "received": recv},
                    "fusion_stats": fstats,
+                   "selfcheck": {"N": ns, "iters": 7, "bit_exact_vs_numpy": selfcheck},
                    "l2_policy": f"grid {(n + 2) ** 2 * 8 / 1e9:.1f} GB (/{world} per GPU) exceeds the "
                                 "126 MB L2; no flush needed" if (n + 2) ** 2 * 8 / world > 2.5e8 else
                                 "per-GPU block near L2 size: numbers include L2 hits"},
@@ -532,6 +542,8 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
                                     "against the bytes the kernels have to move"},
     }
     del grid
+    if not selfcheck:
+        raise RuntimeError("stencil self-check failed: the partitioned / fused path disagrees with NumPy")
     return out
 
 

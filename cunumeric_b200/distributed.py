@@ -185,13 +185,17 @@ class PartitionedArray:
         mine = [t for t in transfers if t.src == runtime.rank or t.dst == runtime.rank]
         if not mine:
             return
+        # Take the pointers BEFORE opening the group: Store.ptr first runs whatever is still deferred
+        # (fused chains and queued halo exchanges, i.e. other NCCL groups), which must neither be
+        # nested inside this group nor be launched after it.
+        src_base, dst_base = m.local.base.ptr, dst.base.ptr
         _comm_check(lib.cnb_comm_group_start())
         for t in mine:
             if t.src == runtime.rank:
-                ptr = m.local.base.ptr + (t.row_lo - (lo - m.halo)) * rb
+                ptr = src_base + (t.row_lo - (lo - m.halo)) * rb
                 _comm_check(lib.cnb_comm_send(comm, ptr, t.nrows * rb, t.dst, stream))
             else:
-                ptr = dst.base.ptr + (t.row_lo - dst_base_row0) * rb
+                ptr = dst_base + (t.row_lo - dst_base_row0) * rb
                 _comm_check(lib.cnb_comm_recv(comm, ptr, t.nrows * rb, t.src, stream))
         _comm_check(lib.cnb_comm_group_end())
 

@@ -32,6 +32,21 @@ def main() -> None:
         assert np.array_equal(w.__array__(), w_np), f"stencil work mismatch n={n}"
         assert np.array_equal(g.__array__(), g_np), f"stencil grid mismatch n={n}"
 
+    # ---- even N: the row pitch is a multiple of 16 bytes -> the chain runs as TMA-staged tiles on each
+    # rank's block, with the halo exchange queued between the deferred chains
+    from cunumeric_b200 import fusion
+
+    for n, iters, dt in ((254, 6, np.float64), (1022, 5, np.float64), (510, 4, np.float32)):
+        before = fusion.stats["tma_launches"]
+        g = stencil_init(n, dt, xp=cn)
+        w = stencil_run(g, iters)
+        g_np = stencil_init(n, dt, xp=np)
+        w_np = stencil_run(g_np, iters)
+        assert np.array_equal(w.__array__(), w_np), f"stencil work mismatch n={n}"
+        assert np.array_equal(g.__array__(), g_np), f"stencil grid mismatch n={n}"
+        if fusion.enabled() and n // world >= 16:
+            assert fusion.stats["tma_launches"] - before >= iters, (n, fusion.stats)
+
     # ---- elementwise on partitioned + replicated operands
     rng = np.random.default_rng(5)
     a = rng.normal(size=(101, 37))
@@ -75,6 +90,46 @@ def main() -> None:
     V = cn.array(v)
     assert int(V.sum()) == int(v.sum()) and int(V.argmax()) == int(v.argmax())
     assert float(X.sum(initial=10.0)) == pytest_approx(x.sum(dtype=np.float64) + 10.0)
+
+    # ---- reductions against the ORACLE (the reference's own functors): value reductions within
+    # n * eps, indices / integer / boolean results exactly, and NaN handling of MAX / MIN independent of
+    # the number of ranks (gather of the partials + the library's own fold, not ncclMax / ncclMin)
+    from oracle import ref
+
+    if ref.available():
+        y = rng.normal(size=(211, 96)).astype(np.float32)
+        y[5, 7] = np.nan
+        y[200, 1] = np.nan
+        Yn = cn.array(y)
+        n_eps = y.size * np.finfo(np.float32).eps
+        for op, fn in (("MAX", lambda a: a.max()), ("MIN", lambda a: a.min())):
+            exp = ref.scalar_unary_red(op, y)
+            got = np.asarray(fn(Yn).__array__())
+            assert np.array_equal(got, exp.reshape(got.shape), equal_nan=True), (op, got, exp)
+            exp0 = ref.unary_red(op, y, 0)
+            got0 = (Yn.max(axis=0) if op == "MAX" else Yn.min(axis=0)).__array__()
+            assert np.array_equal(got0, exp0, equal_nan=True), (op, "axis 0")
+        exp = float(ref.scalar_unary_red("SUM", x))
+        assert abs(float(X.sum()) - exp) <= n_eps * np.abs(x).sum()
+        exp0 = ref.unary_red("SUM", x, 0)
+        assert np.all(np.abs(X.sum(axis=0).__array__() - exp0) <= x.shape[0] * np.finfo(np.float32).eps
+                      * np.abs(x).sum(axis=0))
+        exp1 = ref.unary_red("SUM", x, 1)
+        assert np.all(np.abs(X.sum(axis=1).__array__() - exp1) <= x.shape[1] * np.finfo(np.float32).eps
+                      * np.abs(x).sum(axis=1))
+        am = ref.scalar_unary_red("ARGMAX", x)
+        assert int(X.argmax()) == int(am["arg"])
+        assert np.array_equal(X.argmax(axis=0).__array__(), ref.unary_red("ARGMAX", x, 0)["arg"])
+        assert np.array_equal(X.argmin(axis=1).__array__(), ref.unary_red("ARGMIN", x, 1)["arg"])
+        s16 = rng.integers(-50, 50, size=(64, 33)).astype(np.int16)
+        S16 = cn.array(s16)
+        assert np.array_equal(S16.max(axis=0).__array__(), ref.unary_red("MAX", s16, 0))
+        assert np.array_equal(S16.sum(axis=0).__array__(), ref.unary_red("SUM", s16, 0))
+        assert int(S16.min()) == int(ref.scalar_unary_red("MIN", s16))
+        z = (rng.normal(size=(50, 9)) + 1j * rng.normal(size=(50, 9))).astype(np.complex64)
+        Z = cn.array(z)
+        expz = ref.unary_red("PROD", z, 0)
+        assert np.allclose(Z.prod(axis=0).__array__(), expz, rtol=1e-4)
 
     # ---- BINARY_RED: local fold per row block + AND across ranks
     Y = cn.array(x.copy())

@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE ONLY: the multi-GPU host logic (PartitionedArray, halo exchange queued between
+deferred fused chains, buffer renaming) on CPU — one process per "GPU" under torchrun, the CUDA
+library replaced by tests/sim_backend.SimLib and NCCL send/recv by gloo.  Run by
+tests/test_partitioned_sim.py."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["CUNUMERIC_B200_MIN_PARTITION"] = "1"
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import sim_backend  # noqa: E402
+
+
+class SimCommLib(sim_backend.SimLib):
+    """SimLib + the cnb_comm_* entry points over gloo (grouped send/recv run at group end)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._group = None
+
+    def cnb_comm_unique_id(self, ident):
+        return 0
+
+    def cnb_comm_init(self, ident, world, rank):
+        return 1
+
+    def cnb_comm_group_start(self):
+        self._group = []
+        return 0
+
+    def cnb_comm_send(self, comm, ptr, nbytes, peer, stream):
+        raw = np.frombuffer((ctypes.c_uint8 * nbytes).from_address(ptr), dtype=np.uint8).copy()
+        self._group.append(("send", torch.from_numpy(raw), peer, None))
+        return 0
+
+    def cnb_comm_recv(self, comm, ptr, nbytes, peer, stream):
+        self._group.append(("recv", torch.empty(nbytes, dtype=torch.uint8), peer, ptr))
+        return 0
+
+    def cnb_comm_group_end(self):
+        reqs = []
+        for kind, t, peer, ptr in self._group:
+            reqs.append((dist.isend(t, peer) if kind == "send" else dist.irecv(t, peer), kind, t, ptr))
+        for r, kind, t, ptr in reqs:
+            r.wait()
+            if kind == "recv":
+                ctypes.memmove(ptr, t.numpy().ctypes.data, t.numel())
+        self._group = None
+        return 0
+
+
+def main() -> None:
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+    from cunumeric_b200.distributed import PartitionedArray
+    from cunumeric_b200.workloads import stencil_init, stencil_run
+
+    rt = cn.runtime
+    lib = SimCommLib()
+    rt.lib, rt.stream, rt.device = lib, None, 0
+    rt.rank, rt.world_size, rt.comm = rank, world, 1
+    fusion._lookup = lambda sig: ("sim", sig)
+    fusion._launch = sim_backend.make_fused_launcher(lib, np.random.default_rng(rank))
+    mode = os.environ.get("SIM_FUSION", "always")
+    fusion._mode = mode
+
+    for n, iters in ((30, 3), (13, 5), (64, 4)):
+        g = stencil_init(n, np.float64, xp=cn)
+        assert isinstance(g._thunk, PartitionedArray)
+        w = stencil_run(g, iters)
+        g_np = stencil_init(n, np.float64, xp=np)
+        w_np = stencil_run(g_np, iters)
+        got_w, got_g = w.__array__(), g.__array__()
+        assert np.array_equal(got_g, g_np), f"rank {rank}: grid mismatch n={n} mode={mode}: " \
+            f"{np.argwhere(got_g != g_np)[:4].tolist()}"
+        assert np.array_equal(got_w, w_np), f"rank {rank}: work mismatch n={n} mode={mode}: " \
+            f"{np.argwhere(got_w != w_np)[:4].tolist()}"
+    # a second program: elementwise on shifted row views of a partitioned array, in-place update
+    rng = np.random.default_rng(3)
+    a0 = rng.normal(size=(41, 7))
+    A = cn.array(a0)
+    for _ in range(3):
+        up = A[1:-1] + A[0:-2] + A[2:]      # output aligned with the middle rows: neighbours at +-1
+        A[1:-1] = up * 0.25
+        a0[1:-1] = (a0[1:-1] + a0[0:-2] + a0[2:]) * 0.25
+    assert np.array_equal(A.__array__(), a0), f"rank {rank}: shifted-row update mismatch"
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank} ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -53,7 +53,7 @@ _FOLD_BINOP = {
 class _Shared:
     """State shared by a base array and all of its views."""
 
-    __slots__ = ("gshape", "dtype", "part", "halo", "local", "ghost_valid")
+    __slots__ = ("gshape", "dtype", "part", "halo", "local", "ghost_valid", "align_cache")
 
     def __init__(self, gshape, dtype, part: RowPartition, halo: int) -> None:
         self.gshape = tuple(int(s) for s in gshape)
@@ -63,6 +63,7 @@ class _Shared:
         rows = part.count(runtime.rank) + 2 * self.halo
         self.local = DeferredArray(Store.empty((rows,) + self.gshape[1:], self.dtype))
         self.ghost_valid = False
+        self.align_cache = {}
 
     @property
     def row_bytes(self) -> int:
@@ -74,7 +75,10 @@ def _comm_check(rc: int) -> None:
 
 
 class PartitionedArray:
-    __slots__ = ("meta", "row0", "row1", "inner_key", "host_scalar")
+    # a view is immutable: shape, induced partition, owned rows and the local windows are computed
+    # once (the host cost per NumPy call bounds the iteration rate once the per-GPU work is < 1 ms)
+    __slots__ = ("meta", "row0", "row1", "inner_key", "host_scalar", "_shape", "_part", "_owned",
+                 "_local")
 
     def __init__(self, meta: _Shared, row0: int = 0, row1: Optional[int] = None,
                  inner_key: Tuple = ()) -> None:
@@ -83,6 +87,8 @@ class PartitionedArray:
         self.row1 = meta.gshape[0] if row1 is None else row1
         self.inner_key = inner_key  # basic index applied to dims >= 1 of the local block
         self.host_scalar = None
+        self._shape = self._part = self._owned = None
+        self._local = {}
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -131,17 +137,29 @@ class PartitionedArray:
     @property
     def part(self) -> RowPartition:
         """Partition of THIS view's rows (view coordinates)."""
-        return self.meta.part.window(self.row0, self.row1)
+        p = self._part
+        if p is None:
+            m = self.meta
+            p = self._part = m.part if (self.row0 == 0 and self.row1 == m.gshape[0]) else \
+                m.part.window(self.row0, self.row1)
+        return p
 
     @property
     def owned(self) -> Tuple[int, int]:
-        return self.part.bounds(runtime.rank)
+        o = self._owned
+        if o is None:
+            o = self._owned = self.part.bounds(runtime.rank)
+        return o
 
     @property
     def shape(self) -> Tuple[int, ...]:
-        probe = Store(None, self.meta.dtype, (self.row1 - self.row0,) + self.meta.gshape[1:])
-        return _basic_index(probe, (slice(None),) + self.inner_key).shape if self.inner_key \
-            else probe.shape
+        sh = self._shape
+        if sh is None:
+            sh = (self.row1 - self.row0,) + self.meta.gshape[1:]
+            if self.inner_key:
+                sh = _basic_index(Store(None, self.meta.dtype, sh), (slice(None),) + self.inner_key).shape
+            self._shape = sh
+        return sh
 
     @property
     def ndim(self) -> int:
@@ -162,6 +180,9 @@ class PartitionedArray:
     # ------------------------------------------------------------------ local access
     def local_rows(self, vlo: int, vhi: int) -> DeferredArray:
         """DeferredArray over view rows [vlo, vhi) (must lie inside owned +- halo)."""
+        hit = self._local.get((vlo, vhi))
+        if hit is not None:
+            return hit
         m = self.meta
         lo, hi = m.part.bounds(runtime.rank)
         b0, b1 = self.row0 + vlo, self.row0 + vhi
@@ -169,7 +190,8 @@ class PartitionedArray:
         base = m.local.base.slice(0, slice(b0 - (lo - m.halo), b1 - (lo - m.halo)))
         if self.inner_key:
             base = _basic_index(base, (slice(None),) + self.inner_key)
-        return DeferredArray(base)
+        out = self._local[(vlo, vhi)] = DeferredArray(base)
+        return out
 
     def _invalidate(self) -> None:
         self.meta.ghost_valid = False
@@ -214,6 +236,34 @@ class PartitionedArray:
         # before its temporaries have died.
         fusion.enqueue(lambda: self._run_transfers(plan, lo - m.halo, m.local))
         m.ghost_valid = True
+
+    def _ensure_aligned_with(self, out_part: RowPartition) -> None:
+        """This view is about to be read row for row by a task whose output rows are tiled by
+        `out_part`: make the rows every rank needs available (collective).  The classification is a
+        pure function of the two tilings and is cached on the base array."""
+        m = self.meta
+        key = (out_part, self.row0)
+        kind = m.align_cache.get(key)
+        if kind is None:
+            kind = 0   # 0: owned, 1: within the halo, 2: farther
+            for r in range(out_part.world):
+                a, b = out_part.bounds(r)
+                if b <= a:
+                    continue
+                nlo, nhi = self.row0 + a, self.row0 + b
+                lo, hi = m.part.bounds(r)
+                if nlo < lo - m.halo or nhi > hi + m.halo:
+                    kind = 2
+                    break
+                if nlo < lo or nhi > hi:
+                    kind = 1
+            m.align_cache[key] = kind
+        if kind == 1:
+            self.exchange_halo()
+        elif kind == 2:
+            raise NotImplementedError(
+                "operand rows are farther than the halo depth from their owner: general "
+                "redistribution is not implemented (use gather() / a larger halo)")
 
     def _ensure_rows(self, needs: Sequence[Tuple[int, int]]) -> None:
         """`needs[r]` = BASE rows rank r is about to read.  Collective."""
@@ -264,12 +314,7 @@ class PartitionedArray:
             # partitioned axis): replicate it (collective) and fall through to the replicated rules
             src = src.gather()
         if isinstance(src, PartitionedArray):
-            mine = self.part
-            needs = []
-            for r in range(runtime.world_size):
-                a, b = mine.bounds(r)
-                needs.append((src.row0 + a, src.row0 + b))
-            src._ensure_rows(needs)
+            src._ensure_aligned_with(self.part)
             return src.local_rows(vlo, vhi)
         # replicated operand: scalars and lower-rank / unit-row arrays broadcast, full-height ones
         # are cut to the local rows

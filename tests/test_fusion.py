@@ -400,3 +400,37 @@ def test_default_mode_compiles_on_second_sighting(tmp_path, monkeypatch):
         assert np.array_equal(results[0], results[1]) and np.array_equal(results[1], results[2])
     finally:
         fusion.set_mode(old)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    # (nbytes, offset, rows, row_bytes, pitch) — every word width of the complement kernel
+    (4096, 64, 10, 256, 400),        # 16-byte words
+    (4096 + 8, 72, 10, 248, 392),    # 8-byte words
+    (4000, 36, 9, 100, 404),         # 4-byte words
+    (3001, 7, 11, 113, 257),         # bytes
+    (1 << 20, 4104, 255, 4000, 4104),  # stencil-like: thin gaps, row-sized head and tail
+    (5000, 0, 1, 5000, 5000),        # the window is the whole buffer: nothing to copy
+    (5000, 100, 1, 300, 300),        # single row: head and tail only
+])
+def test_copy_complement_matches_numpy(case):
+    """cnb_copy_complement (write-after-read renaming): dst <- src outside the pitched window, dst
+    untouched inside it."""
+    import ctypes
+
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import _lib
+
+    nbytes, offset, rows, row_bytes, pitch = case
+    rng = pu.rng_for("complement")
+    src_h = rng.integers(0, 256, size=nbytes, dtype=np.uint8)
+    dst_h = np.full(nbytes, 0xEE, dtype=np.uint8)
+    src, dst = cn.array(src_h), cn.array(dst_h)
+    rt = cn.runtime
+    _lib.check(rt.lib.cnb_copy_complement(dst._thunk.base.ptr, src._thunk.base.ptr, nbytes, offset, rows,
+                                          row_bytes, pitch, rt.stream))
+    got = np.array(dst)
+    exp = src_h.copy()
+    for r in range(rows):
+        exp[offset + r * pitch: offset + r * pitch + row_bytes] = 0xEE
+    assert np.array_equal(got, exp), np.flatnonzero(got != exp)[:8]

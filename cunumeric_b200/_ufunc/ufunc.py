@@ -15,11 +15,13 @@ import numpy as np
 from ..config import BinaryOpCode, UnaryOpCode, UnaryRedCode
 from ..deferred import DeferredArray
 from ..runtime import runtime as _runtime
+from ..distributed import _partitioning
 from ..store import Store
 
 
 def _single_gpu() -> bool:
-    return _runtime.world_size == 1
+    """New arrays are plain per-process device arrays: one GPU, or a `replicated()` block."""
+    return _runtime.world_size == 1 or not _partitioning[0]
 
 
 _ndarray_cls: list = []

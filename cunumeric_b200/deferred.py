@@ -280,7 +280,7 @@ class DeferredArray:
     def unary_op_prepared(self, op_code: int, rhs: Store) -> None:
         """unary_op for a freshly allocated output of the operand's shape (the ufunc fast path)."""
         lhs = self.base
-        if fusion.capture("U", int(op_code), lhs, (rhs,)):
+        if fusion.capture("U", op_code, lhs, (rhs,), 0, True):
             return
         d_out, d_in = lhs.descriptor(), rhs.descriptor()
         _lib.check(runtime.lib.cnb_unary_op(int(op_code), ctypes.byref(d_out), None,
@@ -290,7 +290,7 @@ class DeferredArray:
         """binary_op for a freshly allocated output and operands already broadcast to its shape
         (the ufunc fast path): nothing to replicate, no aliasing to resolve, no extra scalars."""
         lhs = self.base
-        if fusion.capture("B", int(op_code), lhs, (rhs1, rhs2)):
+        if fusion.capture("B", op_code, lhs, (rhs1, rhs2), 0, True):
             return
         d_out, d1, d2 = lhs.descriptor(), rhs1.descriptor(), rhs2.descriptor()
         _lib.check(runtime.lib.cnb_binary_op(int(op_code), ctypes.byref(d_out), ctypes.byref(d1),

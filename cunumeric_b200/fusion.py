@@ -90,6 +90,16 @@ class _Window:
                 lo += (n - 1) * s
         self.lo, self.hi = lo, hi + store.dtype.itemsize
 
+    @staticmethod
+    def fresh(store) -> "_Window":
+        """Window of a freshly allocated dense store (Store.empty): offset 0, spans its buffer."""
+        w = object.__new__(_Window)
+        w.buffer = buf = store.buffer
+        w.offset, w.shape, w.strides, w.dtype = 0, store.shape, store.strides, store.dtype
+        w.key = (id(buf), 0, store.shape, store.strides, store.dtype.num)
+        w.lo, w.hi = 0, buf.nbytes
+        return w
+
     def overlaps(self, other: "_Window") -> bool:
         return self.buffer is other.buffer and self.lo < other.hi and other.lo < self.hi
 
@@ -170,9 +180,11 @@ def pending() -> bool:
 # ---------------------------------------------------------------------------------------------
 # capture
 # ---------------------------------------------------------------------------------------------
-def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> bool:
+def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0, fresh: bool = False) -> bool:
     """Try to defer an elementwise task `lhs = kind/op(rhs...)` (stores already broadcast to
-    lhs.shape).  Returns False if the caller must launch it eagerly."""
+    lhs.shape).  Returns False if the caller must launch it eagerly.  `fresh`: lhs was allocated for
+    this task by the ufunc fast path (dense, numeric, the operands already have its shape): nothing
+    can alias it yet, so the checks on the output side are skipped."""
     global _chain
     if _flushing or _mode in ("0", "off", "false"):
         return False
@@ -180,16 +192,20 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
     if runtime.lib is None and not runtime.dry_run:
         runtime.ensure_initialized()  # no device -> fail loudly right here
     shape = lhs.shape
-    if len(shape) > MAX_DIM or lhs.size == 0:
-        return False
-    for n, st in zip(shape, lhs.strides):
-        if st == 0 and n > 1:
+    if fresh:
+        if lhs._size == 0 or len(shape) > MAX_DIM:
             return False
-    if lhs.dtype.kind == "V":  # Argval structs
-        return False
-    for r in rhs:
-        if r.shape != shape or r.dtype.kind == "V":
+    else:
+        if len(shape) > MAX_DIM or lhs.size == 0:
             return False
+        for n, st in zip(shape, lhs.strides):
+            if st == 0 and n > 1:
+                return False
+        if lhs.dtype.kind == "V":  # Argval structs
+            return False
+        for r in rhs:
+            if r.shape != shape or r.dtype.kind == "V":
+                return False
     c = _chain
     if c.tasks and (c.shape != shape or len(c.tasks) >= MAX_TASKS or
                     len(c.ext_index) + len(rhs) > MAX_INPUTS):
@@ -197,7 +213,7 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
         c = _chain
     out_w = lhs._win
     if out_w is None:
-        out_w = lhs._win = _Window(lhs)
+        out_w = lhs._win = _Window.fresh(lhs) if fresh else _Window(lhs)
     in_w = []
     for r in rhs:
         w = r._win
@@ -214,13 +230,15 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0) -> boo
                     if w.lo < ww.hi and ww.lo < w.hi:
                         hazard = True
         bid = id(out_w.buffer)
-        if not hazard and out_w.key not in written:
+        if fresh:
+            pass  # a buffer nobody has seen yet: no write-after-write / write-after-read possible
+        elif not hazard and out_w.key not in written:
             if bid in c.renamed:  # a second write window on a renamed buffer: keep it simple
                 hazard = True
             for ww in c.w_by_buf.get(bid, ()):  # write over a chain output, different window
                 if out_w.lo < ww.hi and ww.lo < out_w.hi:
                     hazard = True
-        if not hazard:
+        if not hazard and not fresh:
             for rw in c.r_by_buf.get(bid, ()):  # write over something read through another window
                 if rw.key != out_w.key and out_w.lo < rw.hi and rw.lo < out_w.hi:
                     war = True

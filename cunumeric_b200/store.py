@@ -23,6 +23,9 @@ def c_strides(shape: Sequence[int], itemsize: int) -> Tuple[int, ...]:
     return tuple(reversed(strides))
 
 
+_STRIDES: dict = {}   # (shape, itemsize) -> C-order byte strides
+
+
 class Store:
     __slots__ = ("buffer", "dtype", "shape", "strides", "offset", "_win", "_size")
 
@@ -71,7 +74,13 @@ class Store:
         st = object.__new__(Store)
         st.buffer = buffer = runtime.allocate(size * dtype.itemsize)
         st.dtype, st.shape, st.offset = dtype, shape, 0
-        st.strides = c_strides(shape, dtype.itemsize)
+        key = (shape, dtype.itemsize)
+        strides = _STRIDES.get(key)
+        if strides is None:
+            if len(_STRIDES) > 4096:
+                _STRIDES.clear()
+            strides = _STRIDES[key] = c_strides(shape, dtype.itemsize)
+        st.strides = strides
         st._win, st._size = None, size
         buffer.users += 1
         return st

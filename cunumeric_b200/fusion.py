@@ -497,7 +497,7 @@ def _replay(c: _Chain, tasks: List[_Task]) -> None:
 # ---------------------------------------------------------------------------------------------
 # kernel lookup / generation / compilation
 # ---------------------------------------------------------------------------------------------
-_GENERATOR_VERSION = 8
+_GENERATOR_VERSION = 10
 _src_tag: List[str] = []
 
 
@@ -525,7 +525,7 @@ def _source_tag() -> str:
 
 def _hash(sig) -> str:
     knobs = "".join(f"{k}={os.environ.get(k, '')};" for k in
-                    ("CNB_FUSED_B", "CNB_FUSED_U", "CNB_FUSED_MINBLOCKS"))
+                    ("CNB_FUSED_B", "CNB_FUSED_U", "CNB_FUSED_MINBLOCKS", "CNB_FUSED_VEC_MINBLOCKS"))
     return hashlib.sha1((_source_tag() + knobs + repr(sig)).encode()).hexdigest()[:20]
 
 
@@ -770,7 +770,42 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
         return "\n".join(s)
 
     # ---- vector kernel
-    L.append(f'extern "C" __global__ void __launch_bounds__({THREADS}) fused_{h}_vec(const __grid_constant__ FPlan plan)\n{{')
+    # issue-bound chains: 5 CTAs / SM (measured best for Black-Scholes: 4 -> 0.54 ms, 5 -> 0.53, 6 spills)
+    vec_min = int(os.environ.get("CNB_FUSED_VEC_MINBLOCKS") or 5)
+    vec_bounds = f"{THREADS}, {vec_min}" if geo["ctas_per_sm"] else f"{THREADS}"
+    L.append(f'extern "C" __global__ void __launch_bounds__({vec_bounds}) fused_{h}_vec(const __grid_constant__ FPlan plan)\n{{')
+    # dense 1-D fast path (plan.vec == 2: one row, every array operand contiguous): no row / tile
+    # arithmetic and no broadcast tests per tile — on an issue-bound chain (Black-Scholes) the generic
+    # per-tile prologue is ~10 % of all instructions
+    L.append("  if (plan.vec == 2) {\n    const int tid = threadIdx.x;")
+    L.append(hoist.replace("\n  ", "\n    ").replace("  Pack", "    Pack", 1) if hoist else "")
+    L.append("    const long long full = plan.inner / TILE;")
+    for k in range(nops):
+        L.append(f"    const long long off{k} = 0;")
+    L.append("    for (long long tile = blockIdx.x; tile < full; tile += gridDim.x) {\n"
+             "      const long long e0 = tile * TILE + (long long)tid * E;")
+    for i in range(n_in):
+        if not scalar_in[i]:
+            L.append(f"      Pack<T{i}, E> a{i}[U];")
+    L.append("#pragma unroll\n      for (int u = 0; u < U; ++u) {")
+    for i in range(n_in):
+        if not scalar_in[i]:
+            L.append(f"        ld_bytes<sizeof(T{i}) * E>(a{i}[u].raw, plan.op[{n_out + i}].ptr + "
+                     f"(e0 + (long long)u * {THREADS} * E) * (long long)sizeof(T{i}));")
+    L.append("      }\n#pragma unroll\n      for (int u = 0; u < U; ++u) {")
+    for j, (v, _) in enumerate(outs):
+        L.append(f"        Pack<T{v}, E> r{j};")
+    args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[u][i_]" for i in range(n_in)] +
+                     [f"r{j}[i_]" for j in range(n_out)])
+    L.append(f"#pragma unroll\n        for (int i_ = 0; i_ < E; ++i_) body({args});")
+    for j, (v, _) in enumerate(outs):
+        L.append(f"        st_bytes<sizeof(T{v}) * E>(plan.op[{j}].ptr + (e0 + (long long)u * {THREADS} * E) * "
+                 f"(long long)sizeof(T{v}), r{j}.raw);")
+    L.append("      }\n    }")
+    L.append("    if (full * TILE < plan.inner && full %% gridDim.x == blockIdx.x) {\n"
+             "      for (long long e = full * TILE + tid; e < plan.inner; e += %d) {" % THREADS)
+    L.append(scalar_elem("        ", "e"))
+    L.append("      }\n    }\n    return;\n  }")
     L.append(head)
     L.append("    if (col0 + TILE > plan.inner) {\n      for (long long e = col0 + tid; e < plan.inner; e += %d) {" % THREADS)
     L.append(scalar_elem("        ", "e"))
@@ -1251,10 +1286,14 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
     E = geo["E"]
     n_out = len(out_windows)
     vec = True
+    dense1d = rows == 1
+    scalar_flags = [False] * n_out + [sc for _, sc in sig[0]]
     for k, w in enumerate(windows):
         size = sizes[k]
         bcast = inner_st[k] == 0 and k >= n_out
         align = size if bcast else min(16, size * E)
+        if bcast and not scalar_flags[k]:
+            dense1d = False     # an array operand broadcast along the row: generic vector path
         if not bcast and inner_st[k] != size and inner != 1:
             vec = False
         # blocks are at least 256-byte aligned: the window offset decides
@@ -1290,7 +1329,7 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
     plan.inner, plan.rows = inner, rows
     plan.tiles_per_row = (inner + out_pad + tile - 1) // tile
     plan.num_tiles = plan.tiles_per_row * rows
-    plan.vec, plan.out_pad = int(vec), out_pad
+    plan.vec, plan.out_pad = (2 if (vec and dense1d and inner != 1) else int(vec)), out_pad
     _lib.check(runtime.lib.cnb_launch_fused(k_vec if vec else k_str, ctypes.byref(plan),
                                             ctypes.sizeof(plan), plan.num_tiles, inner * rows, algo,
                                             ntasks, geo["ctas_per_sm"], runtime.stream))

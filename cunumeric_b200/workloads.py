@@ -101,6 +101,15 @@ def precompile_fused_chains(verbose: bool = False) -> int:
 
     if cn.runtime.lib is not None:
         return 0  # a device is live: chains compile on demand instead
+    # kernels of older generator / header versions are never looked up again: drop them
+    import glob
+    import os
+
+    for path in glob.glob(os.path.join(fusion._CACHE_DIR, "fused_*")):
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
 
     def bs(dtype):
         def run():

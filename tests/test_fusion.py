@@ -409,7 +409,7 @@ def test_default_mode_compiles_on_second_sighting(tmp_path, monkeypatch):
     (4096 + 8, 72, 10, 248, 392),    # 8-byte words
     (4000, 36, 9, 100, 404),         # 4-byte words
     (3001, 7, 11, 113, 257),         # bytes
-    (1 << 20, 4104, 255, 4000, 4104),  # stencil-like: thin gaps, row-sized head and tail
+    (1 << 20, 4104, 254, 4000, 4104),  # stencil-like: thin gaps, row-sized head and tail
     (5000, 0, 1, 5000, 5000),        # the window is the whole buffer: nothing to copy
     (5000, 100, 1, 300, 300),        # single row: head and tail only
 ])

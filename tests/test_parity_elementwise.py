@@ -18,12 +18,32 @@ TRANSCENDENTAL_ULP = 2
 # Complex results are judged NORM-wise: |got - exp| <= k * eps * |exp| (a component-wise ulp count
 # is meaningless when one component is tiny next to the other).  Complex arithmetic beyond
 # add/sub/mul goes through different, equally valid library algorithms on the CPU (libstdc++ /
-# glibc) and the GPU (libcu++); k is the budget in units of eps*|z|.
-COMPLEX_EPS = {"DIVIDE": 4, "POWER": 256, "FLOAT_POWER": 256}
-COMPLEX_UNARY_EPS = 128  # the reference's own tests use allclose(rtol=1e-5) = 168 eps for complex64
+# glibc) and the GPU (libcu++).  Each bound k below is 2x the WORST error observed over four seeded
+# input sets of 10 007 elements (benchmarks/measure_tolerances.py on a B200, round 2; floor 4): the
+# exp / trig / hyperbolic families agree to ~2.5 eps, the log / inverse families differ by 10-180
+# eps where libstdc++ evaluates them through log(1 + ...) compositions that cancel.
+COMPLEX_EPS = {
+    "DIVIDE/complex128": 6, "DIVIDE/complex64": 4, "FLOAT_POWER/complex128": 40,
+    "FLOAT_POWER/complex64": 38, "POWER/complex128": 46, "POWER/complex64": 39,
+}
+COMPLEX_UNARY_EPS = {
+    "ABSOLUTE/complex128": 4, "ABSOLUTE/complex64": 4, "ARCCOS/complex128": 10,
+    "ARCCOS/complex64": 12, "ARCCOSH/complex128": 39, "ARCCOSH/complex64": 40,
+    "ARCSIN/complex128": 108, "ARCSIN/complex64": 149, "ARCSINH/complex128": 53,
+    "ARCSINH/complex64": 74, "ARCTAN/complex128": 357, "ARCTAN/complex64": 25,
+    "ARCTANH/complex128": 89, "ARCTANH/complex64": 122, "COS/complex128": 5, "COS/complex64": 6,
+    "COSH/complex128": 5, "COSH/complex64": 6, "EXP/complex128": 4, "EXP/complex64": 5,
+    "EXP2/complex128": 4, "EXP2/complex64": 5, "EXPM1/complex128": 5, "EXPM1/complex64": 5,
+    "LOG/complex128": 47, "LOG/complex64": 23, "LOG10/complex128": 31, "LOG10/complex64": 21,
+    "LOG1P/complex128": 208, "LOG1P/complex64": 78, "LOG2/complex128": 32, "LOG2/complex64": 29,
+    "RECIPROCAL/complex128": 4, "RECIPROCAL/complex64": 4, "SIN/complex128": 5, "SIN/complex64": 5,
+    "SINH/complex128": 5, "SINH/complex64": 5, "SQRT/complex128": 5, "SQRT/complex64": 5,
+    "TAN/complex128": 6, "TAN/complex64": 6, "TANH/complex128": 6, "TANH/complex64": 6,
+}
 # Real functions whose CPU libm (glibc 2.39, external to the reference) is itself only accurate to
 # ~4 ulp, so agreement within 2 ulp is not attainable by being MORE accurate: glibc's
-# libm-test-ulps lists cbrt (double) at 4 ulp; the device cbrt() is a 1-ulp function.
+# libm-test-ulps lists cbrt (double) at 4 ulp; the device cbrt() is a 1-ulp function (observed
+# worst disagreement: 3 ulp).
 LIBM_LIMITED_ULP = {("CBRT", "float64"): 4}
 
 
@@ -60,7 +80,7 @@ def binary_tolerance(op, dt, odt):
     if dt.kind == "c":
         if op in ("ADD", "SUBTRACT", "MULTIPLY", "MAXIMUM", "MINIMUM"):
             return 0
-        return COMPLEX_EPS.get(op, TRANSCENDENTAL_ULP)
+        return COMPLEX_EPS.get(f"{op}/{dt.name}", TRANSCENDENTAL_ULP)
     if op in pu.EXACT_BINARY:
         return 0
     return TRANSCENDENTAL_ULP
@@ -82,7 +102,7 @@ def test_binary_op(op, dt):
     tol = binary_tolerance(op, dt, odt)
     if dt.kind == "c" and odt.kind == "c" and tol > 0:
         with np.errstate(all="ignore"):
-            pu.assert_close_scaled(got, exp, np.abs(exp), COMPLEX_EPS.get(op, tol), what)
+            pu.assert_close_scaled(got, exp, np.abs(exp), tol, what)
     elif op in ("LOGADDEXP", "LOGADDEXP2") and dt.kind == "f":
         # max(a,b) + log1p(exp(-|a-b|)) cancels when max(a,b) < 0: the 1-ulp differences of
         # exp/log1p are relative to the TERMS, not to the (possibly tiny) result
@@ -140,7 +160,7 @@ def unary_tolerance(op, dt, odt):
     if op in pu.EXACT_UNARY and not (dt.kind == "c" and op in ("ABSOLUTE", "SQRT", "RECIPROCAL")):
         return 0
     if dt.kind == "c":
-        return COMPLEX_UNARY_EPS
+        return COMPLEX_UNARY_EPS.get(f"{op}/{dt.name}", 4)
     return LIBM_LIMITED_ULP.get((op, dt.name), TRANSCENDENTAL_ULP)
 
 

@@ -101,7 +101,7 @@ PROTOTYPES = {
     "cnb_module_load": (_i32, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "cnb_module_get_kernel": (_i32, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cnb_launch_fused": (_i32, [_vp, _vp, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64,
-                                ctypes.c_int64, _i32, _i32, _vp]),
+                                ctypes.c_int64, _i32, _i32, _i32, _vp]),
     "cnb_launch_fused_tma": (_i32, [_vp, ctypes.POINTER(cnb_tma_operand_t), _i32, _vp, _sz, _i32, _i64,
                                     _i64, _i64, _i32, _i32, _vp]),
     "cnb_copy_complement": (_i32, [_vp, _vp, _sz, _i64, _i64, _i64, _i64, _vp]),

@@ -459,6 +459,11 @@ class ndarray:
                                                 res_dtype=np.dtype(np.bool_), out=out,
                                                 keepdims=keepdims, initial=initial, where=where)
 
+    def dot(self, rhs, out=None):
+        from .module import dot
+
+        return dot(self, rhs, out=out)
+
     def mean(self, axis=None, dtype=None, out=None, keepdims=False):
         """array.py:3146-3203: SUM followed by a true_divide."""
         if axis is not None and not isinstance(axis, (int, np.integer)):

@@ -122,7 +122,7 @@ struct HalfShape : Shape<T, T, typename AccOf<T>::type> {
 template <typename T>
 struct All : Shape<T, bool> {
   static constexpr bool valid = !std::is_same<T, c128>::value;
-  __host__ All(const void*) {}
+  __host__ __device__ All(const void*) {}
   __device__ __forceinline__ static bool identity() { return true; }
   __device__ __forceinline__ bool convert(const T& x, long long) const { return nonzero(x); }
   __device__ __forceinline__ static bool fold(bool a, bool b) { return a && b; }
@@ -130,7 +130,7 @@ struct All : Shape<T, bool> {
 template <typename T>
 struct Any : Shape<T, bool> {
   static constexpr bool valid = !std::is_same<T, c128>::value;
-  __host__ Any(const void*) {}
+  __host__ __device__ Any(const void*) {}
   __device__ __forceinline__ static bool identity() { return false; }
   __device__ __forceinline__ bool convert(const T& x, long long) const { return nonzero(x); }
   __device__ __forceinline__ static bool fold(bool a, bool b) { return a || b; }
@@ -138,7 +138,7 @@ struct Any : Shape<T, bool> {
 template <typename T>
 struct CountNonzero : Shape<T, unsigned long long> {
   static constexpr bool valid = true;
-  __host__ CountNonzero(const void*) {}
+  __host__ __device__ CountNonzero(const void*) {}
   __device__ __forceinline__ static unsigned long long identity() { return 0ull; }
   __device__ __forceinline__ unsigned long long convert(const T& x, long long) const
   {
@@ -170,7 +170,7 @@ struct Contains : Shape<T, bool> {
 template <typename T, bool IS_MAX, bool SKIP_NAN>
 struct MinMax : Shape<T, T> {
   static constexpr bool valid = !is_complex_v<T> && (!SKIP_NAN || is_float_v<T>);
-  __host__ MinMax(const void*) {}
+  __host__ __device__ MinMax(const void*) {}
   __device__ __forceinline__ static T identity()
   {
     return IS_MAX ? lowest_of<T>() : highest_of<T>();
@@ -195,7 +195,7 @@ template <typename T, bool SKIP_NAN>
 struct Sum : HalfShape<T> {
   using Acc = typename HalfShape<T>::Acc;
   static constexpr bool valid = !SKIP_NAN || is_float_v<T> || is_complex_v<T>;
-  __host__ Sum(const void*) {}
+  __host__ __device__ Sum(const void*) {}
   __device__ __forceinline__ static Acc identity() { return Acc(0); }
   __device__ __forceinline__ Acc convert(const T& x, long long) const
   {
@@ -211,7 +211,7 @@ struct Prod : HalfShape<T> {
   using Acc = typename HalfShape<T>::Acc;
   static constexpr bool valid = !std::is_same<T, c128>::value &&
                                 (!SKIP_NAN || is_float_v<T> || std::is_same<T, c64>::value);
-  __host__ Prod(const void*) {}
+  __host__ __device__ Prod(const void*) {}
   __device__ __forceinline__ static Acc identity() { return Acc(1); }
   __device__ __forceinline__ Acc convert(const T& x, long long) const
   {

@@ -387,6 +387,12 @@ class DeferredArray:
             fill_value = initial
         else:
             fill_value = _UNARY_RED_IDENTITIES[op](rhs_array.dtype)
+        # map -> reduce fusion: a full reduction of a value the open fused chain produces joins the
+        # chain (fusion.capture_reduce); the pre-fill travels with it as the value to fold into
+        if lhs_array.size == 1 and where is None and not argred and not args and \
+                type(rhs_array) is DeferredArray and \
+                fusion.capture_reduce(int(op), lhs_array.base, rhs_array.base, fill_value):
+            return
         lhs_array.fill(np.array(fill_value, dtype=lhs_array.dtype))
 
         d_in = rhs_array.base.descriptor()

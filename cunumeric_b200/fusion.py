@@ -160,7 +160,8 @@ _flushing = False
 _seen: dict = {}
 _kernels: dict = {}   # signature hash -> (vec kernel, strided kernel, plan class) | None (= unusable)
 stats = {"captured": 0, "fused_launches": 0, "fused_tasks": 0, "replayed_tasks": 0,
-         "elided_tasks": 0, "compiled": 0, "renamed": 0, "deferred": 0, "tma_launches": 0}
+         "elided_tasks": 0, "compiled": 0, "renamed": 0, "deferred": 0, "tma_launches": 0,
+         "fused_reductions": 0}
 
 
 _rt: list = []
@@ -286,6 +287,76 @@ def capture(kind: str, op: int, lhs, rhs: Sequence[Any], nan_op: int = 0, fresh:
     c.written[out_w.key] = (out, out_w)
     c.tasks.append(_Task(kind, int(op), int(nan_op), tuple(ins), out, out_w))
     stats["captured"] += 1
+    return True
+
+
+# reductions that may join a chain as its last step (map -> reduce fusion): value reductions without
+# extra arguments whose accumulator the block-reduce helpers of cnb_reduce.cuh can carry
+MAX_REDUCTIONS = 4
+_FUSABLE_REDS: dict = {}   # UnaryRedCode value -> True, filled on first use
+
+
+def _fusable_red(op: int) -> bool:
+    if not _FUSABLE_REDS:
+        from .config import UnaryRedCode as R
+
+        for code in (R.SUM, R.PROD, R.MAX, R.MIN, R.ALL, R.ANY, R.COUNT_NONZERO, R.NANSUM, R.NANPROD,
+                     R.NANMAX, R.NANMIN):
+            _FUSABLE_REDS[int(code)] = True
+    return int(op) in _FUSABLE_REDS
+
+
+def capture_reduce(op: int, lhs, src, fill_value) -> bool:
+    """Map -> reduce fusion: SCALAR_UNARY_RED of a value the OPEN chain produces (`sum(abs(a - b))`,
+    `(x * y).sum()`, test_map_reduce.py:22-31, the convergence test of test_jacobi.py) joins the
+    chain as a reduce task: the fused kernel folds the value straight out of registers (thread ->
+    warp shuffle -> shared memory -> one partial per CTA -> the last CTA folds the partials in CTA
+    order into the 1-element store), the mapped array itself is only stored if somebody can still
+    observe it.  `lhs`: the 1-element result store; `fill_value`: what the reference pre-fills it
+    with (identity or `initial`, deferred.py:3207-3213).  Returns False if the caller must launch
+    the reduction task eagerly."""
+    if _flushing or _mode in ("0", "off", "false") or not _fusable_red(op):
+        return False
+    c = _chain
+    if not c.tasks or src.shape != c.shape or len(c.tasks) >= MAX_TASKS or \
+            len(c.ext_index) + 1 > MAX_INPUTS or lhs.dtype.kind == "V" or src.dtype.kind == "V":
+        return False
+    if src.dtype not in _PLAIN_DTYPES or src.dtype == np.complex128:
+        return False
+    w = src._win
+    if w is None:
+        w = src._win = _Window(src)
+    hit = c.written.get(w.key)
+    if hit is None:
+        return False   # reducing an array that already lives in memory: the plain kernel does that
+    if sum(1 for t in c.tasks if t.kind == "R") >= MAX_REDUCTIONS:
+        return False
+    out_w = lhs._win
+    if out_w is None:
+        out_w = lhs._win = _Window(lhs)
+    bid = id(out_w.buffer)
+    if bid in c.w_by_buf or bid in c.r_by_buf or out_w.buffer.shared:
+        return False   # the result store is brand-new in every use the API makes of this path
+    from .store import Store
+
+    init = Store.from_scalar(np.array(fill_value, dtype=lhs.dtype)).broadcast_to(c.shape)
+    iw = _Window(init)
+    vid = c.ext_index.get(iw.key)
+    if vid is None:
+        vid = len(c.dtypes)
+        c.dtypes.append(iw.dtype)
+        c.ext.append(iw)
+        c.ext_index[iw.key] = vid
+        c.r_by_buf.setdefault(id(iw.buffer), []).append(iw)
+        iw.buffer.readers += 1
+    out = len(c.dtypes)
+    c.dtypes.append(out_w.dtype)
+    c.ext.append(None)
+    c.w_by_buf.setdefault(bid, []).append(out_w)
+    c.written[out_w.key] = (out, out_w)
+    c.tasks.append(_Task("R", int(op), 0, (hit[0], vid), out, out_w))
+    stats["captured"] += 1
+    stats["fused_reductions"] += 1
     return True
 
 
@@ -478,7 +549,20 @@ def _replay(c: _Chain, tasks: List[_Task]) -> None:
         for v in t.ins:
             w = c.ext[v] if c.ext[v] is not None else produced[v]
             ins.append(w.store())
-        deferred.launch_elementwise(t.kind, t.op, t.nan_op, t.window.store(), ins)
+        if t.kind == "R":
+            # reduce task replayed as the reference issues it: pre-fill the result, then the
+            # SCALAR_UNARY_RED task folds into it
+            from .config import UnaryOpCode
+
+            out_store = t.window.store()
+            first = ins[1]
+            while first.ndim > 0:
+                first = first.project(0, 0)
+            deferred.launch_elementwise("U", int(UnaryOpCode.COPY), 0, out_store,
+                                        [first.broadcast_to(out_store.shape)])
+            deferred.launch_scalar_red(t.op, out_store, ins[0], None, None, None, ())
+        else:
+            deferred.launch_elementwise(t.kind, t.op, t.nan_op, t.window.store(), ins)
         del ins
         produced[t.out] = t.window
         # a dead temporary (no live Store, no later reader in the chain) gives its block back right
@@ -497,7 +581,7 @@ def _replay(c: _Chain, tasks: List[_Task]) -> None:
 # ---------------------------------------------------------------------------------------------
 # kernel lookup / generation / compilation
 # ---------------------------------------------------------------------------------------------
-_GENERATOR_VERSION = 10
+_GENERATOR_VERSION = 11
 _src_tag: List[str] = []
 
 
@@ -598,7 +682,8 @@ def _plan_type(nops: int):
         _fields_ = [("inner", ctypes.c_int64), ("rows", ctypes.c_int64),
                     ("tiles_per_row", ctypes.c_int64), ("num_tiles", ctypes.c_int64),
                     ("vec", ctypes.c_int32), ("out_pad", ctypes.c_int32),
-                    ("op", Operand * nops)]
+                    ("op", Operand * nops),
+                    ("red_partials", ctypes.c_void_p), ("red_ticket", ctypes.c_void_p)]
 
     return Plan
 
@@ -635,9 +720,13 @@ def _geometry(sig):
     in_sizes = [_SIZES[c] for c, _ in in_codes]
     arr_sizes = [_SIZES[c] for c, scalar in in_codes if not scalar]
     out_sizes = [_SIZES[c] for _, c in outs]
-    max_out = max(out_sizes)
+    reds = _reductions(sig)
+    stored = [_SIZES[c] for v, c in outs if v not in reds]   # a fused reduction stores one element
     max_in = max(arr_sizes) if arr_sizes else 1
-    e = max(1, min(16 // max_out, 64 // max_in))
+    if stored:
+        e = max(1, min(16 // max(stored), 64 // max_in))
+    else:
+        e = max(1, 16 // (min(arr_sizes) if arr_sizes else 4))  # store-less: 16 bytes of the narrowest input
     in_bytes = sum(arr_sizes)
     u = max(1, min(8, 128 // max(1, e * in_bytes))) if in_bytes else 4
     # long chains are issue-bound, not memory-bound (Black-Scholes: ~170 instructions per element):
@@ -656,7 +745,8 @@ def _geometry(sig):
         u += 1
     return {"E": e, "U": u, "B": b, "TILE": THREADS * e * u, "in_sizes": in_sizes,
             "out_sizes": out_sizes, "minblocks": int(os.environ.get("CNB_FUSED_MINBLOCKS", "0")),
-            "ctas_per_sm": 6 if heavy else 0}
+            "ctas_per_sm": 6 if heavy else 0,
+            "red_slots": [j for j, (v, _) in enumerate(outs) if v in reds]}
 
 
 def _gen_body(sig, L: List[str]) -> None:
@@ -671,10 +761,14 @@ def _gen_body(sig, L: List[str]) -> None:
         vtype[out] = code
     for v, code in sorted(vtype.items()):
         L.append(f"using T{v} = type_of<{code}>;")
+    reds = _reductions(sig)      # out value id -> (op, source value id, init value id)
     in_params = ", ".join(f"const T{i}& v{i}" for i in range(n_in))
-    out_params = ", ".join(f"T{v}& y{j}" for j, (v, _) in enumerate(outs))
+    # a reduce task's "output" of the per-element body is the element to fold (type of its source)
+    out_params = ", ".join(f"T{reds[v][1] if v in reds else v}& y{j}" for j, (v, _) in enumerate(outs))
     L.append(f"__device__ __forceinline__ void body({in_params}{', ' if in_params else ''}{out_params})\n{{")
     for kind, op, nan_op, ins, out, code in tasks_sig:
+        if kind == "R":
+            continue
         if kind == "B":
             a, b = ins
             L.append(f"  using F{out} = typename BinaryFn<{op}>::template fn<T{a}>;")
@@ -699,8 +793,13 @@ def _gen_body(sig, L: List[str]) -> None:
         else:
             raise ValueError(kind)
     for j, (v, _) in enumerate(outs):
-        L.append(f"  y{j} = v{v};")
+        L.append(f"  y{j} = v{reds[v][1] if v in reds else v};")
     L.append("}")
+
+
+def _reductions(sig) -> dict:
+    """Reduce tasks of a chain signature: {output value id: (redop, source value id, init value id)}."""
+    return {t[4]: (t[1], t[3][0], t[3][1]) for t in sig[1] if t[0] == "R"}
 
 
 def generate_source(sig, h: str) -> str:
@@ -709,15 +808,20 @@ def generate_source(sig, h: str) -> str:
     n_in, n_out = len(in_codes), len(outs)
     nops = n_in + n_out
     E, U, B = geo["E"], geo["U"], geo["B"]
+    reds = _reductions(sig)
+    red_j = [j for j, (v, _) in enumerate(outs) if v in reds]      # output slots that are reductions
     L: List[str] = []
     L.append(f"// generated by cunumeric_b200/fusion.py — fused chain {h}: {len(tasks_sig)} tasks, "
-             f"{n_in} inputs, {n_out} stored outputs")
+             f"{n_in} inputs, {n_out - len(red_j)} stored outputs"
+             + (f", {len(red_j)} fused reduction(s)" if red_j else ""))
     L.append('#include "cnb_elementwise.cuh"\n#include "ops_binary.cuh"\n#include "ops_unary.cuh"\n'
-             '#include "ops_convert.cuh"\nusing namespace cnb;\nnamespace {')
+             '#include "ops_convert.cuh"' + ('\n#include "cnb_reduce.cuh"\n#include "ops_reduce.cuh"' if red_j else "")
+             + '\nusing namespace cnb;\nnamespace {')
     L.append(f"constexpr int NOPS = {nops}, E = {E}, U = {U}, B = {B}, TILE = {THREADS} * E * U;")
     L.append("struct FOperand { char* ptr; long long inner_stride; long long row_stride; };")
+    # red_partials / red_ticket: scratch of the map -> reduce epilogue, filled in by cnb_launch_fused
     L.append("struct FPlan { long long inner, rows, tiles_per_row, num_tiles; int vec, out_pad; "
-             "FOperand op[NOPS]; };")
+             "FOperand op[NOPS]; char* red_partials; unsigned int* red_ticket; };")
     L.append("""template <typename T, int N>
 __device__ __forceinline__ void fload_vec(Pack<T, N>& r, const FOperand& o, long long off, long long e)
 {
@@ -737,6 +841,14 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
 }""")
     scalar_in = [scalar for _, scalar in in_codes]
     _gen_body(sig, L)
+    # element type the body hands out for output slot j (a reduction hands out its SOURCE element)
+    ytype = [f"T{reds[v][1]}" if v in reds else f"T{v}" for v, _ in outs]
+    for j in red_j:
+        v = outs[j][0]
+        op, src, init = reds[v]
+        L.append(f"using R{j} = typename RedFn<{op}>::template fn<T{src}>;")
+        L.append(f"static_assert(R{j}::valid && !R{j}::needs_index && sizeof(typename R{j}::Acc) <= 16 && "
+                 f"std::is_same<typename R{j}::Val, T{v}>::value, \"reduce task {v}\");")
     L.append("}  // namespace")
 
     # operand k: outputs 0..n_out-1, inputs n_out..nops-1
@@ -745,8 +857,9 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
 
     hoist = "".join(f"  Pack<T{i}, 1> s{i};\n  ld_bytes<sizeof(T{i})>(s{i}.raw, plan.op[{n_out + i}].ptr);\n"
                     for i in range(n_in) if scalar_in[i])
-    head = """  const int tid = threadIdx.x;
-""" + hoist + """  for (long long tile = blockIdx.x; tile < plan.num_tiles; tile += gridDim.x) {
+    hoist += "".join(f"  const R{j} red{j}(nullptr);\n  typename R{j}::Acc acc{j} = R{j}::identity();\n"
+                     for j in red_j)
+    tile_loop = """  for (long long tile = blockIdx.x; tile < plan.num_tiles; tile += gridDim.x) {
     long long row = 0, ct = tile;
     if (plan.rows > 1) {
       row = tile / plan.tiles_per_row;
@@ -755,18 +868,86 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
     const long long col0 = ct * TILE;
 """ + rowoffs() + "\n"
 
+    def consume(ind: str, idx: str, addr) -> List[str]:
+        """After body(): fold the reduction slots, store the others.  `idx`: element index into the
+        r{j} packs ("" = whole pack, for vector stores); `addr(j)`: store address of slot j."""
+        s = []
+        for j in red_j:
+            s.append(f"{ind}acc{j} = R{j}::fold(acc{j}, red{j}.convert(r{j}[{idx or 0}], 0));")
+        return s
+
     def scalar_elem(ind: str, e: str) -> str:
         s = []
         for i in range(n_in):
             if not scalar_in[i]:
                 s.append(f"{ind}Pack<T{i}, 1> a{i};\n{ind}fload_one<T{i}>(a{i}, plan.op[{n_out + i}], off{n_out + i}, {e});")
-        for j, (v, _) in enumerate(outs):
-            s.append(f"{ind}Pack<T{v}, 1> r{j};")
+        for j in range(n_out):
+            s.append(f"{ind}Pack<{ytype[j]}, 1> r{j};")
         args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[0]" for i in range(n_in)] +
                          [f"r{j}[0]" for j in range(n_out)])
         s.append(f"{ind}body({args});")
+        s += consume(ind, "0", None)
         for j, (v, _) in enumerate(outs):
-            s.append(f"{ind}st_bytes<sizeof(T{v})>(plan.op[{j}].ptr + off{j} + {e} * plan.op[{j}].inner_stride, r{j}.raw);")
+            if j not in red_j:
+                s.append(f"{ind}st_bytes<sizeof(T{v})>(plan.op[{j}].ptr + off{j} + {e} * plan.op[{j}].inner_stride, r{j}.raw);")
+        return "\n".join(s)
+
+    def vector_chunk(ind: str, load, addr_expr) -> List[str]:
+        """U chunks of E elements per thread: all loads first, then compute + fold / store."""
+        s = []
+        for i in range(n_in):
+            if not scalar_in[i]:
+                s.append(f"{ind}Pack<T{i}, E> a{i}[U];")
+        s.append(f"#pragma unroll\n{ind}for (int u = 0; u < U; ++u) {{")
+        s.append(f"{ind}  const long long e = {addr_expr};")
+        for i in range(n_in):
+            if not scalar_in[i]:
+                s.append(f"{ind}  " + load(i))
+        s.append(f"{ind}}}\n#pragma unroll\n{ind}for (int u = 0; u < U; ++u) {{")
+        s.append(f"{ind}  const long long e = {addr_expr};")
+        for j in range(n_out):
+            s.append(f"{ind}  Pack<{ytype[j]}, E> r{j};")
+        args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[u][i_]" for i in range(n_in)] +
+                         [f"r{j}[i_]" for j in range(n_out)])
+        s.append(f"#pragma unroll\n{ind}  for (int i_ = 0; i_ < E; ++i_) {{\n{ind}    body({args});")
+        s += consume(ind + "    ", "i_", None)
+        s.append(f"{ind}  }}")
+        for j, (v, _) in enumerate(outs):
+            if j not in red_j:
+                s.append(f"{ind}  st_bytes<sizeof(T{v}) * E>(plan.op[{j}].ptr + off{j} + e * (long long)sizeof(T{v}), r{j}.raw);")
+        s.append(f"{ind}}}")
+        return s
+
+    def epilogue() -> str:
+        """map -> reduce: block fold, one partial per CTA, the last CTA (ticket) folds the partials in
+        CTA order into the pre-filled 1-element result (reduce-accessor semantics) — the finishing
+        step of scalar_red.inl, once per fused reduction."""
+        if not red_j:
+            return ""
+        s = ["  {", "    __shared__ bool is_last;"]
+        for n, j in enumerate(red_j):
+            s.append(f"    __shared__ RawSmem<typename R{j}::Acc, RED_WARPS> rs{j};")
+            s.append(f"    acc{j} = block_reduce<R{j}>(acc{j}, rs{j}.ptr());")
+        s.append("    if (threadIdx.x == 0) {")
+        for n, j in enumerate(red_j):
+            s.append(f"      *reinterpret_cast<typename R{j}::Acc*>(plan.red_partials + "
+                     f"((size_t){n} * gridDim.x + blockIdx.x) * 16) = acc{j};")
+        s.append("      __threadfence();\n      is_last = atomicAdd(plan.red_ticket, 1u) == gridDim.x - 1;\n    }")
+        s.append("    __syncthreads();\n    if (is_last) {\n      __threadfence();")
+        s.append(f"      const int per = ((int)gridDim.x + {THREADS} - 1) / {THREADS};\n"
+                 "      const int lo = (int)threadIdx.x * per, hi = min(lo + per, (int)gridDim.x);")
+        for n, j in enumerate(red_j):
+            v = outs[j][0]
+            init = reds[v][2]
+            s.append(f"      {{\n        typename R{j}::Acc total = R{j}::identity();\n"
+                     f"        for (int i = lo; i < hi; ++i) {{\n          typename R{j}::Acc p;\n"
+                     f"          ld_bytes<sizeof(p)>(&p, plan.red_partials + ((size_t){n} * gridDim.x + i) * 16);\n"
+                     f"          total = R{j}::fold(total, p);\n        }}\n"
+                     f"        total = block_reduce<R{j}>(total, rs{j}.ptr());\n"
+                     f"        if (threadIdx.x == 0)\n"
+                     f"          *reinterpret_cast<T{v}*>(plan.op[{j}].ptr) = "
+                     f"R{j}::finish(R{j}::fold(R{j}::lift(s{init}[0]), total));\n      }}")
+        s.append("      if (threadIdx.x == 0) *plan.red_ticket = 0;\n    }\n  }")
         return "\n".join(s)
 
     # ---- vector kernel
@@ -774,64 +955,41 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
     vec_min = int(os.environ.get("CNB_FUSED_VEC_MINBLOCKS") or 5)
     vec_bounds = f"{THREADS}, {vec_min}" if geo["ctas_per_sm"] else f"{THREADS}"
     L.append(f'extern "C" __global__ void __launch_bounds__({vec_bounds}) fused_{h}_vec(const __grid_constant__ FPlan plan)\n{{')
+    L.append("  const int tid = threadIdx.x;\n" + hoist)
     # dense 1-D fast path (plan.vec == 2: one row, every array operand contiguous): no row / tile
     # arithmetic and no broadcast tests per tile — on an issue-bound chain (Black-Scholes) the generic
     # per-tile prologue is ~10 % of all instructions
-    L.append("  if (plan.vec == 2) {\n    const int tid = threadIdx.x;")
-    L.append(hoist.replace("\n  ", "\n    ").replace("  Pack", "    Pack", 1) if hoist else "")
-    L.append("    const long long full = plan.inner / TILE;")
+    L.append("  if (plan.vec == 2) {\n    const long long full = plan.inner / TILE;")
     for k in range(nops):
         L.append(f"    const long long off{k} = 0;")
-    L.append("    for (long long tile = blockIdx.x; tile < full; tile += gridDim.x) {\n"
-             "      const long long e0 = tile * TILE + (long long)tid * E;")
-    for i in range(n_in):
-        if not scalar_in[i]:
-            L.append(f"      Pack<T{i}, E> a{i}[U];")
-    L.append("#pragma unroll\n      for (int u = 0; u < U; ++u) {")
-    for i in range(n_in):
-        if not scalar_in[i]:
-            L.append(f"        ld_bytes<sizeof(T{i}) * E>(a{i}[u].raw, plan.op[{n_out + i}].ptr + "
-                     f"(e0 + (long long)u * {THREADS} * E) * (long long)sizeof(T{i}));")
-    L.append("      }\n#pragma unroll\n      for (int u = 0; u < U; ++u) {")
-    for j, (v, _) in enumerate(outs):
-        L.append(f"        Pack<T{v}, E> r{j};")
-    args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[u][i_]" for i in range(n_in)] +
-                     [f"r{j}[i_]" for j in range(n_out)])
-    L.append(f"#pragma unroll\n        for (int i_ = 0; i_ < E; ++i_) body({args});")
-    for j, (v, _) in enumerate(outs):
-        L.append(f"        st_bytes<sizeof(T{v}) * E>(plan.op[{j}].ptr + (e0 + (long long)u * {THREADS} * E) * "
-                 f"(long long)sizeof(T{v}), r{j}.raw);")
-    L.append("      }\n    }")
+    L.append("    for (long long tile = blockIdx.x; tile < full; tile += gridDim.x) {")
+    L += vector_chunk(
+        "      ",
+        lambda i: f"ld_bytes<sizeof(T{i}) * E>(a{i}[u].raw, plan.op[{n_out + i}].ptr + e * (long long)sizeof(T{i}));",
+        f"tile * TILE + ((long long)u * {THREADS} + tid) * E")
+    L.append("    }")
     L.append("    if (full * TILE < plan.inner && full %% gridDim.x == blockIdx.x) {\n"
              "      for (long long e = full * TILE + tid; e < plan.inner; e += %d) {" % THREADS)
     L.append(scalar_elem("        ", "e"))
-    L.append("      }\n    }\n    return;\n  }")
-    L.append(head)
+    L.append("      }\n    }\n  } else {")
+    L.append(tile_loop)
     L.append("    if (col0 + TILE > plan.inner) {\n      for (long long e = col0 + tid; e < plan.inner; e += %d) {" % THREADS)
     L.append(scalar_elem("        ", "e"))
     L.append("      }\n      continue;\n    }")
-    for i in range(n_in):
-        if not scalar_in[i]:
-            L.append(f"    Pack<T{i}, E> a{i}[U];")
-    L.append("#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const long long e = col0 + (long long)(u * %d + tid) * E;" % THREADS)
-    for i in range(n_in):
-        if not scalar_in[i]:
-            L.append(f"      fload_vec<T{i}, E>(a{i}[u], plan.op[{n_out + i}], off{n_out + i}, e);")
-    L.append("    }\n#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const long long e = col0 + (long long)(u * %d + tid) * E;" % THREADS)
-    for j, (v, _) in enumerate(outs):
-        L.append(f"      Pack<T{v}, E> r{j};")
-    args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[u][i_]" for i in range(n_in)] +
-                     [f"r{j}[i_]" for j in range(n_out)])
-    L.append(f"#pragma unroll\n      for (int i_ = 0; i_ < E; ++i_) body({args});")
-    for j, (v, _) in enumerate(outs):
-        L.append(f"      st_bytes<sizeof(T{v}) * E>(plan.op[{j}].ptr + off{j} + e * (long long)sizeof(T{v}), r{j}.raw);")
-    L.append("    }\n  }\n}")
+    L += vector_chunk(
+        "    ",
+        lambda i: f"fload_vec<T{i}, E>(a{i}[u], plan.op[{n_out + i}], off{n_out + i}, e);",
+        f"col0 + (long long)(u * {THREADS} + tid) * E")
+    L.append("  }\n  }")
+    L.append(epilogue())
+    L.append("}")
 
     # ---- strided kernel (coalesced element accesses, batches of B, store-aligned rows)
     v0 = outs[0][0]
     lb = f"{THREADS}, {geo['minblocks']}" if geo["minblocks"] else f"{THREADS}"
     L.append(f'extern "C" __global__ void __launch_bounds__({lb}) fused_{h}_str(const __grid_constant__ FPlan plan)\n{{')
-    L.append(head)
+    L.append("  const int tid = threadIdx.x;\n" + hoist)
+    L.append(tile_loop)
     L.append(f"""    constexpr int N = E * U;
     long long shift = 0;
     if (plan.out_pad != 0)
@@ -847,14 +1005,18 @@ __device__ __forceinline__ void fload_one(Pack<T, 1>& r, const FOperand& o, long
         if not scalar_in[i]:
             L.append(f"          fload_one<T{i}>(a{i}[j], plan.op[{n_out + i}], off{n_out + i}, e);")
     L.append("        }\n      }\n#pragma unroll\n      for (int j = 0; j < B; ++j) {\n        const long long e = tbase + (long long)(j0 + j) * %d + tid;\n        if (j0 + j < N && e >= 0 && e < plan.inner) {" % THREADS)
-    for j, (v, _) in enumerate(outs):
-        L.append(f"          Pack<T{v}, 1> r{j};")
+    for j in range(n_out):
+        L.append(f"          Pack<{ytype[j]}, 1> r{j};")
     args = ", ".join([f"s{i}[0]" if scalar_in[i] else f"a{i}[j][0]" for i in range(n_in)] +
                      [f"r{j}[0]" for j in range(n_out)])
     L.append(f"          body({args});")
+    L += consume("          ", "0", None)
     for j, (v, _) in enumerate(outs):
-        L.append(f"          st_bytes<sizeof(T{v})>(plan.op[{j}].ptr + off{j} + e * plan.op[{j}].inner_stride, r{j}.raw);")
-    L.append("        }\n      }\n    }\n  }\n}")
+        if j not in red_j:
+            L.append(f"          st_bytes<sizeof(T{v})>(plan.op[{j}].ptr + off{j} + e * plan.op[{j}].inner_stride, r{j}.raw);")
+    L.append("        }\n      }\n    }\n  }")
+    L.append(epilogue())
+    L.append("}")
     return "\n".join(L) + "\n"
 
 
@@ -1277,7 +1439,9 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
 
     k_vec, k_str, plan_cls, geo, _, sig = entry
     windows = list(out_windows) + list(in_windows)
-    dims = _canonical(shape, [w.strides for w in windows])
+    red_slots = geo["red_slots"]
+    zero = (0,) * len(shape)
+    dims = _canonical(shape, [zero if k in red_slots else w.strides for k, w in enumerate(windows)])
     if len(dims) > 2:
         return False
     inner, inner_st = dims[-1]
@@ -1289,6 +1453,8 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
     dense1d = rows == 1
     scalar_flags = [False] * n_out + [sc for _, sc in sig[0]]
     for k, w in enumerate(windows):
+        if k in red_slots:
+            continue            # 1-element result of a fused reduction: written once by one thread
         size = sizes[k]
         bcast = inner_st[k] == 0 and k >= n_out
         align = size if bcast else min(16, size * E)
@@ -1300,7 +1466,7 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
         if w.offset % align or row_st[k] % align:
             vec = False
     tma = None
-    if not vec and _TMA:
+    if not vec and _TMA and not red_slots:
         tma = _tma_layout(sig, shape, out_windows, in_windows, dims)
         if tma is not None and _lookup_tma(sig, tma[0]) is None:
             tma = None
@@ -1324,7 +1490,7 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
         plan.op[k].row_stride = row_st[k]
     tile = geo["TILE"]
     out_pad = 0
-    if not vec and inner_st[0] == sizes[0] and sizes[0] < 128:
+    if not vec and 0 not in red_slots and inner_st[0] == sizes[0] and sizes[0] < 128:
         out_pad = 128 // sizes[0] - 1
     plan.inner, plan.rows = inner, rows
     plan.tiles_per_row = (inner + out_pad + tile - 1) // tile
@@ -1332,7 +1498,7 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
     plan.vec, plan.out_pad = (2 if (vec and dense1d and inner != 1) else int(vec)), out_pad
     _lib.check(runtime.lib.cnb_launch_fused(k_vec if vec else k_str, ctypes.byref(plan),
                                             ctypes.sizeof(plan), plan.num_tiles, inner * rows, algo,
-                                            ntasks, geo["ctas_per_sm"], runtime.stream))
+                                            ntasks, geo["ctas_per_sm"], len(red_slots), runtime.stream))
     commit()
     stats["fused_launches"] += 1
     stats["fused_tasks"] += ntasks

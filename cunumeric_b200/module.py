@@ -216,6 +216,38 @@ def where(a, x=None, y=None) -> ndarray:
     return ndarray._perform_where(mask, x, y)
 
 
+where_ = where
+
+
+# ---------------------------------------------------------------------- dot (1-D inner product)
+def dot(a, b, out=None):
+    """module.py:4235 `dot`, the vector case: sum(a * b) without conjugation — the reference's DOT
+    task (matrix/dot.cu:24-41: a block reduction of lhs * rhs).  Here it is MULTIPLY + SCALAR_UNARY_RED
+    through the thunk layer, which the fusion layer runs as ONE map -> reduce kernel: the products
+    never reach memory.  0-d operands multiply; matrix products (>= 2-D) belong to the BLAS part of
+    the reference, outside the hot-path scope."""
+    a, b = convert_to_cunumeric_ndarray(a), convert_to_cunumeric_ndarray(b)
+    if a.ndim == 0 or b.ndim == 0:
+        from ._ufunc import multiply
+
+        return multiply(a, b, out=out)
+    if a.ndim != 1 or b.ndim != 1:
+        raise NotImplementedError("dot of arrays with more than one dimension (matrix products) is "
+                                  "outside the hot-path scope (SURVEY §2.1: BLAS)")
+    if a.shape != b.shape:
+        raise ValueError(f"shapes {a.shape} and {b.shape} not aligned")
+    common = ndarray.find_common_type(a, b)
+    if common == np.bool_:
+        result = (a & b).any()
+    else:
+        prod = a._maybe_convert(common) * b._maybe_convert(common)
+        result = prod.sum()
+    if out is not None:
+        out._thunk.copy(result._thunk, deep=True)
+        return out
+    return result
+
+
 # ---------------------------------------------------------------------- reductions
 def sum(a, axis=None, dtype=None, out=None, keepdims=False, initial=None, where=None):
     return convert_to_cunumeric_ndarray(a).sum(axis=axis, dtype=dtype, out=out,
@@ -273,6 +305,14 @@ def count_nonzero(a, axis=None):
                                             res_dtype=np.dtype(np.uint64))
 
 
+def numpy_compat() -> bool:
+    """settings.py:79-89 `CUNUMERIC_NUMPY_COMPATIBILITY`: issue the additional tasks that make
+    nanmin / nanmax / nanargmin / nanargmax behave like NumPy on all-NaN slices."""
+    import os
+
+    return os.environ.get("CUNUMERIC_NUMPY_COMPATIBILITY", "0").lower() in ("1", "true", "yes", "on")
+
+
 def _nan_red(op: UnaryRedCode, fallback: UnaryRedCode):
     def fn(a, axis=None, out=None, keepdims=False, initial=None, where=None, dtype=None):
         a = convert_to_cunumeric_ndarray(a)
@@ -282,7 +322,19 @@ def _nan_red(op: UnaryRedCode, fallback: UnaryRedCode):
         kwargs = dict(axis=axis, out=out, keepdims=keepdims, initial=initial, where=where)
         if op in (UnaryRedCode.NANSUM, UnaryRedCode.NANPROD):
             kwargs["dtype"] = dtype
-        return ndarray._perform_unary_reduction(code, a, **kwargs)
+        result = ndarray._perform_unary_reduction(code, a, **kwargs)
+        if op in (UnaryRedCode.NANMAX, UnaryRedCode.NANMIN) and numpy_compat() and a.dtype.kind == "f":
+            # module.py:6022-6024 / 6118-6120: an all-NaN slice yields NaN, as in NumPy (the plain
+            # reduction leaves the finite identity there); putmask == where(all_nan, nan, result)
+            from ._ufunc import isnan
+
+            all_nan = all(isnan(a), axis=axis, keepdims=keepdims, where=where)
+            fixed = where_(all_nan, np.nan, result)
+            if out is not None:
+                out._thunk.copy(fixed._thunk, deep=True)
+                return out
+            return fixed
+        return result
 
     return fn
 
@@ -296,6 +348,15 @@ nanmin = _nan_red(UnaryRedCode.NANMIN, UnaryRedCode.MIN)
 def _nan_argred(op: UnaryRedCode, fallback: UnaryRedCode):
     def fn(a, axis=None, out=None, keepdims=False):
         a = convert_to_cunumeric_ndarray(a)
+        if a.size == 0:
+            raise ValueError(f"attempt to get {'nanargmax' if op == UnaryRedCode.NANARGMAX else 'nanargmin'}"
+                             " of an empty sequence")
+        if numpy_compat() and a.dtype.kind == "f":
+            # module.py:5850-5852 / 5918-5920
+            from ._ufunc import isnan
+
+            if bool(any(all(isnan(a), axis=axis))):
+                raise ValueError("Array/Slice contains only NaNs")
         code = op if a.dtype.kind == "f" else fallback
         return a._argred(code, axis, out, keepdims)
 

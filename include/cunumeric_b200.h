@@ -260,10 +260,13 @@ const char* cnb_version(void);
 #define CNB_OP_FUSED 1000
 int cnb_module_load(const void* image, size_t bytes, void** module);
 int cnb_module_get_kernel(void* module, const char* name, void** kernel);
-/* max_ctas_per_sm: resident CTAs per SM the persistent grid may use (0 = the memory-bound default, 3) */
+/* max_ctas_per_sm: resident CTAs per SM the persistent grid may use (0 = the memory-bound default, 3).
+ * n_reductions > 0: the chain ends in that many SCALAR_UNARY_RED tasks (map -> reduce fusion,
+ * scalar_unary_red_template.inl:84-118 folded into the producing kernel); the last 16 bytes of
+ * `plan` are then overwritten with the reduction scratch {partials, ticket}. */
 int cnb_launch_fused(void* kernel, const void* plan, size_t plan_bytes, int64_t num_tiles,
                      int64_t elements, int64_t algorithmic_bytes, int32_t ntasks,
-                     int32_t max_ctas_per_sm, void* stream);
+                     int32_t max_ctas_per_sm, int32_t n_reductions, void* stream);
 /* TMA-staged flavour of a fused chain (north_star: "TMA-staged tiles for strided and transposed"
  * operands; replaces the per-element div/mod walk of the reference's generic kernels,
  * binary/binary_op.cu:33-52, pitches.h:46-55, for pitched 2-D views).  Every pitched operand buffer

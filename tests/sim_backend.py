@@ -25,6 +25,19 @@ UNARY = {
 }
 
 
+from cunumeric_b200.config import UnaryRedCode  # noqa: E402
+
+# fused reduce tasks: fold(pre-fill, reduce(source))
+REDUCE = {
+    int(UnaryRedCode.SUM): lambda init, x: init + x.sum(dtype=x.dtype),
+    int(UnaryRedCode.PROD): lambda init, x: init * x.prod(dtype=x.dtype),
+    int(UnaryRedCode.MAX): lambda init, x: np.maximum(init, x.max()),
+    int(UnaryRedCode.MIN): lambda init, x: np.minimum(init, x.min()),
+    int(UnaryRedCode.ALL): lambda init, x: np.logical_and(init, x.all()),
+    int(UnaryRedCode.ANY): lambda init, x: np.logical_or(init, x.any()),
+}
+
+
 def _window(ptr, dtype, shape, strides):
     """NumPy view of device (= host) memory described by a base pointer and byte strides."""
     dtype = np.dtype(dtype)
@@ -154,6 +167,9 @@ def make_fused_launcher(lib: SimLib, schedule_rng=None):
         with np.errstate(all="ignore"):
             for kind, op, nan_op, ins, out, code in tasks:
                 args = [vals[v] for v in ins]
+                if kind == "R":
+                    vals[out] = np.asarray(REDUCE[op](np.asarray(args[1]).flat[0], args[0])).astype(DTYPES[code]).reshape(())
+                    continue
                 if kind == "B":
                     r = BINARY[op](*args)
                 elif kind == "U":
@@ -176,6 +192,8 @@ def make_fused_launcher(lib: SimLib, schedule_rng=None):
         outs_v = [window_view(w, p) for w, p in zip(out_windows, ptrs[:n_out])]
         ins_v = [window_view(w, p) for w, p in zip(in_windows, ptrs[n_out:])]
         mode = int(rng.integers(3)) if len(shape) >= 1 and shape[0] > 1 else 0
+        if any(t[0] == "R" for t in sig[1]):
+            mode = 0   # a reduction spans the rows: evaluate the chain in one piece
         if mode == 0:
             vals = evaluate(sig, {i: v.copy() for i, v in enumerate(ins_v)})
             for (v, code), o in zip(outs, outs_v):

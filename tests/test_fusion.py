@@ -434,3 +434,90 @@ def test_copy_complement_matches_numpy(case):
     for r in range(rows):
         exp[offset + r * pitch: offset + r * pitch + row_bytes] = 0xEE
     assert np.array_equal(got, exp), np.flatnonzero(got != exp)[:8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float64, np.float32, np.float16, np.int32, np.int64],
+                         ids=lambda d: np.dtype(d).name)
+def test_map_reduce_fusion_against_the_oracle(dt):
+    """A full reduction of a value the chain produces runs inside the fused kernel
+    (fusion.capture_reduce).  Bars of the reduction suites: MAX / MIN / ALL / integer sums exact, floating
+    sums within n * eps of the oracle (the reference's functors + its sequential fold)."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+    from oracle import ref
+
+    dt = np.dtype(dt)
+    rng = pu.rng_for("map-reduce", dt.name)
+    n = 70001
+    a0 = pu.make_input(dt, n, rng, "small")
+    b0 = pu.make_input(dt, n, rng, "small")
+    a, b = cn.array(a0), cn.array(b0)
+    old = fusion.set_mode("always")
+    try:
+        before = dict(fusion.stats)
+        l0 = cn.runtime.launch_count()
+        delta = cn.sum(cn.absolute(a - b))
+        cn.flush()
+        assert cn.runtime.launch_count() - l0 == 1          # one kernel: no fill, no reduction launch
+        t = a * b
+        mx, mn = t.max(), t.min()
+        pos = (t > 0).any()
+        d = cn.dot(a, b)
+        got = [np.array(v) for v in (delta, mx, mn, pos, d, t)]
+        stats = {k: fusion.stats[k] - before[k] for k in before}
+    finally:
+        fusion.set_mode(old)
+    assert stats["fused_reductions"] == 5 and stats["replayed_tasks"] == 0
+    diff = ref.unary_op("ABSOLUTE", ref.binary_op("SUBTRACT", a0, b0))
+    prod = ref.binary_op("MULTIPLY", a0, b0)
+    assert np.array_equal(got[5], prod)
+    exp_sum = ref.scalar_unary_red("SUM", diff)
+    exp_dot = ref.scalar_unary_red("SUM", prod)
+    if dt.kind in "iu":
+        assert got[0] == exp_sum and got[4] == exp_dot
+    else:
+        eps = float(np.finfo(dt).eps)
+        for g, e, terms in ((got[0], exp_sum, diff), (got[4], exp_dot, prod)):
+            assert abs(float(g) - float(e)) <= n * eps * np.abs(terms.astype(np.float64)).sum()
+    assert got[1] == ref.scalar_unary_red("MAX", prod) and got[2] == ref.scalar_unary_red("MIN", prod)
+    assert bool(got[3]) == bool((prod > 0).any())
+
+
+@pytest.mark.gpu
+def test_jacobi_with_convergence_test_in_the_loop():
+    """tests/integration/test_jacobi.py:23-57 of the reference: `delta = sum(abs(work - center))`
+    inside the iteration.  The whole iteration — 4 ADD, MULTIPLY, SUBTRACT, ABSOLUTE, the SUM and the
+    COPY back into the (renamed) grid — is one kernel."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    def program(xp, n, iters):
+        grid = xp.zeros((n + 2, n + 2), np.float32)
+        grid[:, 0] = -273.15
+        grid[:, -1] = -273.15
+        grid[-1, :] = -273.15
+        grid[0, :] = 40.0
+        center, north, east = grid[1:-1, 1:-1], grid[0:-2, 1:-1], grid[1:-1, 2:]
+        west, south = grid[1:-1, 0:-2], grid[2:, 1:-1]
+        deltas = []
+        for _ in range(iters):
+            average = center + north + east + west + south
+            work = 0.2 * average
+            deltas.append(xp.sum(xp.absolute(work - center)))
+            center[:] = work
+        return grid, [float(d) for d in deltas]
+
+    old = fusion.set_mode("always")
+    try:
+        before = dict(fusion.stats)
+        g, deltas = program(cn, 10, 2)           # the reference's own vector: 10 x 10, 2 iterations
+        g2, deltas2 = program(cn, 300, 5)
+        stats = {k: fusion.stats[k] - before[k] for k in before}
+    finally:
+        fusion.set_mode(old)
+    g_np, deltas_np = program(np, 10, 2)
+    assert np.array_equal(np.array(g), g_np) and np.allclose(deltas, deltas_np, rtol=1e-5)
+    g2_np, deltas2_np = program(np, 300, 5)
+    assert np.array_equal(np.array(g2), g2_np) and np.allclose(deltas2, deltas2_np, rtol=1e-5)
+    assert stats["fused_reductions"] == 7 and stats["renamed"] == 7 and stats["replayed_tasks"] == 0

@@ -187,3 +187,29 @@ def test_opaque_steps_keep_program_order(sim):
     assert log == [] or log == [("step", 24.0)]
     assert np.array_equal(np.array(c), np.full((3, 4), 6.0))
     assert log == [("step", 24.0)]
+
+
+def test_map_reduce_joins_the_chain(sim):
+    """sum(abs(a - b)) (the convergence test of test_jacobi.py) and dot(a, b): the reduction is the
+    chain's last task, the mapped temporaries never reach memory."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200 import fusion
+
+    rng = np.random.default_rng(0)
+    a0, b0 = rng.normal(size=(13, 7)), rng.normal(size=(13, 7))
+    a, b = cn.array(a0), cn.array(b0)
+    before = dict(fusion.stats)
+    fused0, launches0 = sim.fused_launches, sim.launches
+    delta = cn.sum(cn.absolute(a - b))
+    got = float(delta)
+    assert np.isclose(got, np.abs(a0 - b0).sum(), rtol=1e-12)
+    d = {k: fusion.stats[k] - before[k] for k in before}
+    assert d["fused_reductions"] == 1 and sim.fused_launches - fused0 == 1
+    assert sim.launches - launches0 == 1                 # no fill, no separate reduction launch
+    assert sim.stored_outputs[-1] == 1                   # only the 1-element result
+    # max with `initial`, and a mapped array that stays observable next to its reduction
+    t = a * b
+    m = t.max(initial=0.5)
+    assert float(m) == max(0.5, (a0 * b0).max()) and np.array_equal(np.array(t), a0 * b0)
+    x0, y0 = rng.normal(size=257), rng.normal(size=257)
+    assert np.isclose(float(cn.dot(cn.array(x0), cn.array(y0))), np.dot(x0, y0), rtol=1e-12)

@@ -486,9 +486,11 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
     timer.begin()
     sampler.mark_begin()
     launches0 = cn.runtime.launch_count()
+    t_issue = time.perf_counter()
     for _ in range(steps):
         stencil_run(grid, iters)
         cn.flush()  # nothing stays pending: the step's last iteration is issued inside the timed region
+    t_issue = time.perf_counter() - t_issue   # host time to ISSUE the work (launches are asynchronous)
     elapsed = timer.end()
     sampler.mark_end()
     launches = cn.runtime.launch_count() - launches0
@@ -524,6 +526,7 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
                                 "op-by-op)" if fused_on else "; issued op-by-op, one kernel per task"),
                    "execution": "fused" if fused_on else "op-by-op",
                    "N": n, "iters_per_step": iters, "ms_per_iteration": 1e3 * elapsed / steps / iters,
+                   "host_issue_ms_per_iteration": 1e3 * t_issue / steps / iters,
                    "algorithmic_bytes_per_point": round(bytes_per_point, 3),
                    "collective": ("ncclSend/ncclRecv of one ghost row per neighbour per iteration "
                                   "(grouped, stream-ordered)" if world > 1 else "none (1 GPU)"),

@@ -228,7 +228,10 @@ class PartitionedArray:
             m.ghost_valid = True
             return
         lo, _ = m.part.bounds(runtime.rank)
-        plan = plan_halo(m.part, m.halo)
+        plan = m.align_cache.get("halo_plan")
+        if plan is None:
+            plan = m.align_cache["halo_plan"] = [t for t in plan_halo(m.part, m.halo)
+                                                 if t.src == runtime.rank or t.dst == runtime.rank]
         # The exchange keeps its place in program order between the deferred fused chains
         # (fusion.enqueue): it reads the rows the previous chain writes and fills the ghosts the
         # next chain reads, and takes its pointers when it runs — the base buffer may have been
@@ -308,14 +311,14 @@ class PartitionedArray:
     # ------------------------------------------------------------------ operand alignment
     def _operand(self, src: Any, vlo: int, vhi: int) -> DeferredArray:
         """Local piece of `src` aligned with this (output) view's rows [vlo, vhi)."""
-        if isinstance(src, PartitionedArray) and (src.ndim != self.ndim or
-                                                  src.shape[0] != self.shape[0]):
+        if type(src) is PartitionedArray:
+            sshape, myshape = src.shape, self.shape
+            if len(sshape) == len(myshape) and sshape[0] == myshape[0]:
+                src._ensure_aligned_with(self.part)
+                return src.local_rows(vlo, vhi)
             # cannot be aligned row-for-row with the output (lower rank, or broadcast along the
             # partitioned axis): replicate it (collective) and fall through to the replicated rules
             src = src.gather()
-        if isinstance(src, PartitionedArray):
-            src._ensure_aligned_with(self.part)
-            return src.local_rows(vlo, vhi)
         # replicated operand: scalars and lower-rank / unit-row arrays broadcast, full-height ones
         # are cut to the local rows
         if src.ndim == self.ndim and self.ndim > 0 and src.shape[0] == self.shape[0] \

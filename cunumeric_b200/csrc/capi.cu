@@ -2,11 +2,17 @@
 // per-opcode-group translation units.
 #include "cnb_common.cuh"
 
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 
 namespace cnb {
 int ensure_init();
+void* pool_alloc(size_t nbytes, cudaStream_t stream);
+int pool_free(void* p, cudaStream_t stream);
 
 #define CNB_DECL_BIN(N) \
   int binary_group##N(int, const cnb_store_t*, const cnb_store_t*, const cnb_store_t*, const void*, cudaStream_t);
@@ -51,6 +57,194 @@ int check_store(const cnb_store_t* s, const char* name)
 
 std::mutex g_redop_mu;
 std::map<int32_t, int32_t> g_argval_types;  // type_uid -> element dtype code
+
+int axis_red_dispatch(int op, int axis, const cnb_store_t* out, const cnb_store_t* in,
+                      const cnb_store_t* where, long long axis_origin, cudaStream_t s)
+{
+  int rc;
+  if ((rc = axis_red_group1(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
+  if ((rc = axis_red_group2(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
+  if ((rc = axis_red_group3(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
+  if ((rc = axis_red_group4(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
+  if ((rc = axis_red_group5(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
+  if (op == CNB_RED_CONTAINS)
+    return set_error(CNB_ERR_INVALID_OP, "CONTAINS exists on the scalar path only");
+  return set_error(CNB_ERR_BAD_ARG, "unknown reduction opcode %d", op);
+}
+
+// ---- a few very long rows: split each row over several CTAs -------------------------------------
+// ROW mode (the axis is the contiguous dim) gives one CTA (or one pipeline slot) per OUTPUT element.
+// With fewer outputs than half the SMs — sum(axis=1) of an (8, 1e8) array — most of the chip idles
+// (the reference sizes its grid to an occupancy wave regardless of the shape, unary_red.cu:148-161).
+// Such a task is run in two stages with the same kernels: stage 1 reduces S segments of every row
+// into a [outputs x S] scratch of partials (pre-filled with the identity), stage 2 reduces the
+// scratch along S into the caller's (pre-filled) output.  Value reductions only: an arg-reduction's
+// partial is an Argval, which no kernel takes as input.
+int second_stage_op(int op)
+{
+  switch (op) {
+    case CNB_RED_SUM:
+    case CNB_RED_NANSUM:
+    case CNB_RED_COUNT_NONZERO: return CNB_RED_SUM;
+    case CNB_RED_PROD:
+    case CNB_RED_NANPROD: return CNB_RED_PROD;
+    case CNB_RED_MAX:
+    case CNB_RED_NANMAX: return CNB_RED_MAX;
+    case CNB_RED_MIN:
+    case CNB_RED_NANMIN: return CNB_RED_MIN;
+    case CNB_RED_ALL: return CNB_RED_ALL;
+    case CNB_RED_ANY: return CNB_RED_ANY;
+    default: return -1;
+  }
+}
+
+// identity of the SECOND-stage reduction on partials of dtype `code` (what stage 1 folds into)
+bool partial_identity(int op2, int code, unsigned char* buf)
+{
+  std::memset(buf, 0, 16);
+  auto put = [&](auto v) { std::memcpy(buf, &v, sizeof(v)); };
+  const bool is_max = op2 == CNB_RED_MAX, is_min = op2 == CNB_RED_MIN;
+  switch (op2) {
+    case CNB_RED_SUM:
+    case CNB_RED_ANY: return true;  // all-zero bytes
+    case CNB_RED_ALL: put((unsigned char)1); return code == CNB_BOOL;
+    case CNB_RED_PROD:
+      switch (code) {
+        case CNB_BOOL:
+        case CNB_INT8:
+        case CNB_UINT8: put((unsigned char)1); return true;
+        case CNB_INT16:
+        case CNB_UINT16: put((uint16_t)1); return true;
+        case CNB_INT32:
+        case CNB_UINT32: put((uint32_t)1); return true;
+        case CNB_INT64:
+        case CNB_UINT64: put((uint64_t)1); return true;
+        case CNB_FLOAT16: put((uint16_t)0x3c00); return true;
+        case CNB_FLOAT32: put(1.0f); return true;
+        case CNB_FLOAT64: put(1.0); return true;
+        case CNB_COMPLEX64: put(1.0f); return true;  // (1, 0)
+        default: return false;
+      }
+    default: break;
+  }
+  if (!is_max && !is_min) return false;
+  switch (code) {  // MAX: the lowest value, MIN: the highest
+    case CNB_BOOL: put((unsigned char)(is_max ? 0 : 1)); return true;
+    case CNB_INT8: put((int8_t)(is_max ? INT8_MIN : INT8_MAX)); return true;
+    case CNB_INT16: put((int16_t)(is_max ? INT16_MIN : INT16_MAX)); return true;
+    case CNB_INT32: put((int32_t)(is_max ? INT32_MIN : INT32_MAX)); return true;
+    case CNB_INT64: put((int64_t)(is_max ? INT64_MIN : INT64_MAX)); return true;
+    case CNB_UINT8: put((uint8_t)(is_max ? 0 : UINT8_MAX)); return true;
+    case CNB_UINT16: put((uint16_t)(is_max ? 0 : UINT16_MAX)); return true;
+    case CNB_UINT32: put((uint32_t)(is_max ? 0 : UINT32_MAX)); return true;
+    case CNB_UINT64: put((uint64_t)(is_max ? 0 : UINT64_MAX)); return true;
+    case CNB_FLOAT16: put((uint16_t)(is_max ? 0xfc00 : 0x7c00)); return true;   // -inf / +inf
+    case CNB_FLOAT32: put(is_max ? -HUGE_VALF : HUGE_VALF); return true;
+    case CNB_FLOAT64: put(is_max ? -HUGE_VAL : HUGE_VAL); return true;
+    default: return false;  // complex MAX / MIN: lexicographic identities, not worth the special case
+  }
+}
+
+// returns 1 if the task was not split (the caller runs it as usual), else the status of the split run
+int try_split_long_rows(int op, int axis, const cnb_store_t* out, const cnb_store_t* in,
+                        cudaStream_t s)
+{
+  static const bool enabled = [] {
+    const char* e = getenv("CNB_AXIS_ROW_SPLIT");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const int op2 = second_stage_op(op);
+  if (!enabled || op2 < 0 || in->ndim < 2 || in->ndim + 1 > CNB_MAX_DIM || axis < 0 || axis >= in->ndim)
+    return 1;
+  const long long isz = (long long)dtype_size(in->dtype);
+  const long long vsz = (long long)dtype_size(out->dtype);
+  const long long alen = in->shape[axis];
+  if (in->strides[axis] != isz || out->dtype >= CNB_NUM_DTYPES) return 1;
+  long long nout = 1;
+  for (int d = 0; d < in->ndim; ++d)
+    if (d != axis) nout *= in->shape[d];
+  const int sms = sm_count();
+  if (nout <= 0 || nout * 2 >= sms || alen * isz < (32LL << 20)) return 1;   // >= 32 MiB per row
+  // every kept dim must be slower than the axis (true ROW mode), else COLUMN mode splits already
+  for (int d = 0; d < in->ndim; ++d)
+    if (d != axis && in->shape[d] > 1 && std::llabs(in->strides[d]) < alen * isz) return 1;
+  unsigned char ident[16];
+  if (!partial_identity(op2, out->dtype, ident)) return 1;
+  // Stage 1 views every row as a (Q x W) matrix and reduces it along Q — COLUMN mode: all CTAs sweep
+  // the row front to back together, so the pages in flight stay a compact window (splitting a row
+  // into S far-apart contiguous segments, one CTA each, thrashes the TLB: measured 3.5-4.0 TB/s) —
+  // into W partials per row (+1 for the ragged tail); stage 2 reduces the partials along the row.
+  const long long W = std::max<long long>(1024, 65536 / isz);        // 64 KiB wide
+  const long long Q = alen / W, tail = alen - Q * W;
+  const long long P = W + (tail > 0 ? 1 : 0);                          // partials per output
+  if (Q < 8) return 1;
+
+  char* scratch = static_cast<char*>(pool_alloc((size_t)(nout * P * vsz), s));
+  if (scratch == nullptr) return CNB_ERR_CUDA;
+  int rc = CNB_OK;
+  {
+    cnb_store_t flat{};
+    flat.ptr = scratch; flat.dtype = out->dtype; flat.ndim = 1;
+    flat.shape[0] = nout * P; flat.strides[0] = vsz;
+    rc = fill_value(&flat, ident, s);
+  }
+  // scratch strides of the kept dims: row-major over them, P partials per output
+  long long kstride[CNB_MAX_DIM];
+  {
+    long long acc = P * vsz;
+    for (int d = in->ndim - 1; d >= 0; --d) {
+      if (d == axis) continue;
+      kstride[d] = acc;
+      acc *= in->shape[d];
+    }
+  }
+  // stage 1, one launch per output row: a dense (Q x W) matrix reduced along Q takes the fast COLUMN
+  // kernel (every thread owns its columns outright, 7 TB/s); handing all rows to one launch would
+  // add a second kept dim and fall to the general column kernel (measured 3.4 TB/s)
+  {
+    long long idx[CNB_MAX_DIM] = {0, 0, 0, 0};
+    for (long long r = 0; r < nout && rc == CNB_OK; ++r) {
+      long long in_off = 0, sc_off = 0;
+      for (int d = 0; d < in->ndim; ++d)
+        if (d != axis) {
+          in_off += idx[d] * in->strides[d];
+          sc_off += idx[d] * kstride[d];
+        }
+      cnb_store_t i2{}, o2{};
+      i2.ptr = static_cast<char*>(in->ptr) + in_off; i2.dtype = in->dtype; i2.ndim = 2;
+      i2.shape[0] = Q; i2.strides[0] = W * isz;
+      i2.shape[1] = W; i2.strides[1] = isz;
+      o2.ptr = scratch + sc_off; o2.dtype = out->dtype; o2.ndim = 2;
+      o2.shape[0] = Q; o2.strides[0] = 0;
+      o2.shape[1] = W; o2.strides[1] = vsz;
+      rc = axis_red_dispatch(op, 0, &o2, &i2, nullptr, 0, s);
+      for (int d = in->ndim - 1; d >= 0; --d) {   // next output row
+        if (d == axis) continue;
+        if (++idx[d] < in->shape[d]) break;
+        idx[d] = 0;
+      }
+    }
+  }
+  if (rc == CNB_OK && tail > 0) {
+    // the ragged end of every row: one more partial (ROW mode over `tail` elements)
+    cnb_store_t i2 = *in, o2 = *out;
+    i2.ptr = static_cast<char*>(in->ptr) + Q * W * isz;
+    i2.shape[axis] = tail;
+    o2.ptr = scratch + W * vsz; o2.shape[axis] = tail;
+    for (int d = 0; d < in->ndim; ++d) o2.strides[d] = d == axis ? 0 : kstride[d];
+    rc = axis_red_dispatch(op, axis, &o2, &i2, nullptr, 0, s);
+  }
+  if (rc == CNB_OK) {
+    cnb_store_t i3 = *in, o3 = *out;
+    i3.ptr = scratch; i3.dtype = out->dtype;
+    for (int d = 0; d < in->ndim; ++d) i3.strides[d] = d == axis ? vsz : kstride[d];
+    i3.shape[axis] = P;
+    o3.shape[axis] = P;
+    rc = axis_red_dispatch(op2, axis, &o3, &i3, nullptr, 0, s);
+  }
+  pool_free(scratch, s);
+  return rc;
+}
 }  // namespace
 }  // namespace cnb
 
@@ -158,15 +352,11 @@ int cnb_unary_red(int32_t op, int32_t axis, const cnb_store_t* out, const cnb_st
   if (in->dtype >= CNB_NUM_DTYPES) return set_error(CNB_ERR_BAD_ARG, "reduction on a struct dtype");
   set_task_tag(CNB_OP_UNARY_RED, op, in->dtype);
   auto s = (cudaStream_t)stream;
-  int rc;
-  if ((rc = axis_red_group1(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
-  if ((rc = axis_red_group2(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
-  if ((rc = axis_red_group3(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
-  if ((rc = axis_red_group4(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
-  if ((rc = axis_red_group5(op, axis, out, in, where, axis_origin, s)) != 1) return rc;
-  if (op == CNB_RED_CONTAINS)
-    return set_error(CNB_ERR_INVALID_OP, "CONTAINS exists on the scalar path only");
-  return set_error(CNB_ERR_BAD_ARG, "unknown reduction opcode %d", op);
+  if (where == nullptr) {
+    const int rc = try_split_long_rows(op, axis, out, in, s);
+    if (rc != 1) return rc;
+  }
+  return axis_red_dispatch(op, axis, out, in, where, axis_origin, s);
 }
 
 int cnb_binary_red(int32_t op, const cnb_store_t* out, const cnb_store_t* in1,

@@ -311,3 +311,43 @@ def test_more_scalar_reductions_in_flight_than_scratch_slots():
         outs.append(out)
     for a, o in zip(arrays, outs):
         assert int(o.__numpy_array__()) == int(a.sum())
+
+
+@pytest.mark.parametrize("op", ["SUM", "PROD", "MAX", "MIN", "NANSUM", "NANMAX", "ALL", "ANY",
+                                "COUNT_NONZERO", "ARGMAX"])
+@pytest.mark.parametrize("shape,dt", [((3, 1 << 23), np.float32), ((2, 3, (1 << 22) + 77), np.float64),
+                                      ((5, (1 << 25) + 3), np.int8), ((2, 1 << 22), np.complex64)],
+                         ids=["3xf32", "2x3xf64", "5xi8", "2xc64"])
+def test_few_very_long_rows_are_split_across_ctas(op, shape, dt):
+    """ROW mode with fewer outputs than SMs / 2: value reductions run in two stages —
+    S segments per row into a scratch of partials, then the scratch along S — so the whole chip works
+    on 3 rows; arg-reductions (partials would be Argvals) keep one CTA per row.  Same bars as the
+    rest of the file, against the oracle."""
+    dt = np.dtype(dt)
+    if ref.red_val_dtype(op, dt) is None:
+        pytest.skip("invalid pair")
+    try:
+        ref.red_identity(op, dt)
+    except ref.InvalidOp:
+        pytest.skip("reference marks this (op, dtype) invalid")
+    rng = pu.rng_for("long-rows", op, dt.name, shape)
+    if op in ("PROD", "NANPROD"):
+        a = np.ones(shape, dtype=dt)
+        idx = rng.integers(0, shape[-1], 40)
+        a[..., idx] = np.asarray(rng.uniform(0.5, 2.0, 40)).astype(dt)
+    elif dt.kind == "c":
+        a = (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(dt)
+    elif dt.kind == "i":
+        a = rng.integers(-5, 6, size=shape).astype(dt)
+    else:
+        a = rng.normal(size=shape).astype(dt)
+    if op.startswith("NAN") and dt.kind == "f":
+        a[..., ::1001] = np.nan
+    if op == "ALL":
+        a[a == 0] = 1
+        a[0, ..., shape[-1] // 2] = 0        # exactly one zero, in the middle segment of row 0
+    axis = len(shape) - 1
+    with np.errstate(all="ignore"):
+        exp = ref.unary_red(op, a, axis)
+    got = thunk_reduce(op, a, axis=axis)
+    check_reduction(op, a, got, exp, shape[-1], f"{op}/{dt.name}/{shape}")

@@ -161,7 +161,7 @@ _seen: dict = {}
 _kernels: dict = {}   # signature hash -> (vec kernel, strided kernel, plan class) | None (= unusable)
 stats = {"captured": 0, "fused_launches": 0, "fused_tasks": 0, "replayed_tasks": 0,
          "elided_tasks": 0, "compiled": 0, "renamed": 0, "deferred": 0, "tma_launches": 0,
-         "fused_reductions": 0}
+         "fused_reductions": 0, "tma_refused": 0}
 
 
 _rt: list = []
@@ -1336,9 +1336,13 @@ def _launch_tma(sig, lay, groups, inner, rows, row_st, out_windows, in_windows, 
         if e is None:
             tail.scalar[n] = ptrs[n_out + i]
             n += 1
-    _lib.check(runtime.lib.cnb_launch_fused_tma(kern, ops, ng, ctypes.byref(tail), ctypes.sizeof(tail),
-                                                geo["smem"], tail.num_tiles, inner * rows, algo, ntasks,
-                                                2, runtime.stream))
+    rc = runtime.lib.cnb_launch_fused_tma(kern, ops, ng, ctypes.byref(tail), ctypes.sizeof(tail),
+                                          geo["smem"], tail.num_tiles, inner * rows, algo, ntasks, 2,
+                                          runtime.stream)
+    if rc == -4:     # CNB_ERR_UNSUPPORTED: the driver refused a tensor map — the strided flavour serves
+        stats["tma_refused"] += 1
+        return False
+    _lib.check(rc)
     return True
 
 

@@ -527,3 +527,65 @@ def test_jacobi_with_convergence_test_in_the_loop():
     assert np.array_equal(np.array(g2), g2_np) and np.allclose(deltas2, deltas2_np, rtol=1e-5)
     # (the boundary fills of the two grids are single-task chains: those replay op-by-op)
     assert stats["fused_reductions"] == 7 and stats["renamed"] == 7 and stats["fused_launches"] >= 7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_tma_flavour_random_shift_groups(seed):
+    """Randomised layouts for the TMA-staged flavour: windows of one or two pitched buffers at random
+    (row, column) shifts, random dtypes (1 / 2 / 4 / 8-byte elements), ragged extents, optional dense
+    third operand and scalar, one or two outputs (dense or a pitched, misaligned window).  Fused ==
+    op-by-op bit for bit, whichever flavour the launcher picks."""
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(1000 + seed)
+    dt = np.dtype([np.float64, np.float32, np.float16, np.int32, np.int8, np.uint16][seed % 6])
+    align = max(1, 16 // dt.itemsize)
+    rows = int(rng.integers(16, 90))
+    inner = int(rng.integers(64, 400))
+    pad_r, pad_c = 4, int(rng.integers(1, 3)) * align        # room for shifts; pitch stays 16-byte multiple
+    width = -(-(inner + 2 * pad_c) // align) * align
+    shape = (rows + 2 * pad_r, width)
+
+    def data(shp):
+        if dt.kind == "f":
+            return rng.normal(size=shp).astype(dt)
+        return rng.integers(-20, 20, size=shp).astype(dt) if dt.kind == "i" else \
+            rng.integers(0, 40, size=shp).astype(dt)
+
+    a0, b0, c0 = data(shape), data(shape), data((rows, inner))
+    shifts = [(int(rng.integers(0, 2 * pad_r + 1)), int(rng.integers(0, width - inner + 1)))
+              for _ in range(int(rng.integers(2, 6)))]
+    out_shift = (int(rng.integers(0, 2 * pad_r + 1)), int(rng.integers(0, width - inner + 1)))
+    use_b, use_c, pitched_out = rng.random() < 0.5, rng.random() < 0.5, rng.random() < 0.5
+
+    def prog():
+        a, b, c = cn.array(a0), cn.array(b0), cn.array(c0)
+        acc = None
+        for k, (r, col) in enumerate(shifts):
+            src = b if (use_b and k % 2) else a
+            v = src[r:r + rows, col:col + inner]
+            acc = v if acc is None else (acc + v if k % 3 else acc - v)
+        if use_c:
+            acc = acc * c
+        res = acc + acc if dt.kind != "f" else acc * 0.5
+        outs = [res]
+        if pitched_out:
+            dst = cn.array(b0)
+            dst[out_shift[0]:out_shift[0] + rows, out_shift[1]:out_shift[1] + inner] = res
+            outs.append(dst)
+        if dt.kind == "f":
+            outs.append(res > 0)
+        return outs
+
+    fused, eager, delta = run_both(prog)
+    assert_identical(fused, eager)
+    assert delta["fused_launches"] >= 1 and delta["tma_refused"] == 0
+    # a window that does not start on a 16-byte boundary rules the vector flavour out: TMA tiles then
+    misaligned = any((c * dt.itemsize) % 16 for _, c in shifts) or \
+        (pitched_out and (out_shift[1] * dt.itemsize) % 16 != 0)
+    # ... provided every pitched operand's row pitch is a multiple of 16 bytes (the dense `c` has
+    # pitch = inner * itemsize)
+    tma_able = not use_c or (inner * dt.itemsize) % 16 == 0
+    if misaligned and tma_able and inner >= 64 and rows >= 16:
+        assert delta["tma_launches"] >= 1, (delta, shifts)

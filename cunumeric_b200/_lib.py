@@ -107,6 +107,7 @@ PROTOTYPES = {
     "cnb_copy_complement": (_i32, [_vp, _vp, _sz, _i64, _i64, _i64, _i64, _vp]),
     "cnb_last_error": (ctypes.c_char_p, []),
     "cnb_version": (ctypes.c_char_p, []),
+    "cnb_argval_fold": (_i32, [_i32, _i32, _vp, _vp, _i32, _i64, _vp]),
     "cnb_comm_unique_id": (_i32, [_vp]),
     "cnb_comm_init": (_vp, [_vp, _i32, _i32]),
     "cnb_comm_destroy": (_i32, [_vp]),

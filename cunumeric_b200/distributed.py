@@ -8,8 +8,8 @@ get_item / set_item — by running the single-GPU task on the local block.  The 
 performs implicitly are explicit, stream-ordered NCCL calls over NVLink:
   * shifted-slice operands (the stencil's north/south views): one grouped send/recv halo refresh per
     producer->consumer step (partition.plan_halo), re-done only after the base array was written;
-  * scalar reductions: local partial -> ncclAllReduce (arg-reductions: max/min of the values, then
-    min of the candidate indices, which is the lowest-index tie-break of the sequential fold);
+  * scalar reductions: local partial -> ncclAllReduce (arg-reductions: ncclAllGather of the 16-byte
+    {index, value} partials + one fold kernel with the lowest-index tie-break of the sequential fold);
   * axis-0 reductions (the partitioned axis): full-width local partial -> ncclAllReduce;
     reductions along other axes need no communication.
 Everything the partition logic decides is a pure function of replicated metadata
@@ -622,37 +622,16 @@ def _allreduce(partial: DeferredArray, op: UnaryRedCode, argred: bool, elem: np.
             return _gather_fold(partial, red)
         _nccl_allreduce(partial, red)
         return partial
-    # arg-reductions: best value across ranks, then the LOWEST index among the ranks that hold it
-    is_max = op in (UnaryRedCode.ARGMAX, UnaryRedCode.NANARGMAX)
-    vals = DeferredArray(Store.empty(partial.shape, elem))
-    vals.copy(_field_view(partial, "arg_value"), deep=True)
-    best = DeferredArray(Store.empty(partial.shape, elem))
-    best.copy(vals, deep=True)
-    red = UnaryRedCode.MAX if is_max else UnaryRedCode.MIN
-    if _needs_gather_fold(best.dtype, red):
-        best = _gather_fold(best, red)
-    else:
-        _nccl_allreduce(best, red)
-    args = DeferredArray(Store.empty(partial.shape, np.int64))
-    args.copy(_field_view(partial, "arg"), deep=True)
-    hit = DeferredArray(Store.empty(partial.shape, np.bool_))
-    hit.binary_op(BinaryOpCode.EQUAL, vals, best)
-    valid = DeferredArray(Store.empty(partial.shape, np.bool_))
-    none = DeferredArray(Store.from_scalar(np.array(np.iinfo(np.int64).min, dtype=np.int64)))
-    valid.binary_op(BinaryOpCode.NOT_EQUAL, args, none)
-    hit.binary_op(BinaryOpCode.LOGICAL_AND, hit, valid)
-    big = DeferredArray(Store.from_scalar(np.array(np.iinfo(np.int64).max, dtype=np.int64)))
-    cand = DeferredArray(Store.empty(partial.shape, np.int64))
-    cand.where(hit, args, big)
-    _nccl_allreduce(cand, UnaryRedCode.MIN)
-    # no rank had a real element -> keep the identity index
-    has = DeferredArray(Store.empty(partial.shape, np.bool_))
-    has.binary_op(BinaryOpCode.NOT_EQUAL, cand, big)
-    final_arg = DeferredArray(Store.empty(partial.shape, np.int64))
-    final_arg.where(has, cand, none)
+    # arg-reductions: ncclAllGather of the 16-byte {index, value} partials, then ONE kernel folds them in
+    # rank order with the reduction's own tie-breaking (lowest global index; cnb_argval_fold)
+    assert partial.base.is_c_contiguous
+    world = runtime.world_size
+    gathered = DeferredArray(Store.empty((world,) + tuple(partial.shape), partial.dtype))
+    _lib.check(runtime.lib.cnb_comm_allgather(runtime.comm, partial.base.ptr, gathered.base.ptr,
+                                              partial.size * partial.dtype.itemsize, runtime.stream))
     out = DeferredArray(Store.empty(partial.shape, partial.dtype))
-    _field_view(out, "arg").copy(final_arg, deep=True)
-    _field_view(out, "arg_value").copy(best, deep=True)
+    _lib.check(runtime.lib.cnb_argval_fold(int(op), dtype_code(elem), out.base.ptr, gathered.base.ptr,
+                                           world, partial.size, runtime.stream))
     return out
 
 

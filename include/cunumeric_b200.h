@@ -299,6 +299,12 @@ int cnb_copy_complement(void* dst, const void* src, size_t nbytes, int64_t offse
  * copies / future-map folds; here they are explicit, stream-ordered NCCL calls.
  * ------------------------------------------------------------------------------------------- */
 #define CNB_COMM_ID_BYTES 128
+/* Fold of per-rank arg-reduction partials gathered in rank order (world x n Argval<T>, 16 bytes each)
+ * into n Argvals, with the tie-breaking of ArgmaxReduction / ArgminReduction (arg.inl:43-50: the
+ * incumbent survives ties, i.e. the lowest global index).  In the reference Legion folds the partial
+ * futures / reduction instances with the registered redop (arg_redop_register.cc:21-46). */
+int cnb_argval_fold(int32_t op, int32_t elem_dtype, void* out, const void* gathered, int32_t world,
+                    int64_t n, void* stream);
 int cnb_comm_unique_id(void* id_out /* CNB_COMM_ID_BYTES */);
 void* cnb_comm_init(const void* id, int32_t nranks, int32_t rank);
 int cnb_comm_destroy(void* comm);

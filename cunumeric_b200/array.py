@@ -160,13 +160,14 @@ class ndarray:
             raise NotImplementedError("asynchronous to_host of a partitioned array")
         return self._thunk.to_host_async(out)
 
-    def to_host_rows(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def to_host_rows(self, out: Optional[np.ndarray] = None, blocking: bool = True):
         """Counterpart of from_host_rows: THIS rank's block of rows (the whole array on one GPU),
-        copied into `out` (e.g. pinned) without any inter-GPU traffic."""
+        copied into `out` (e.g. pinned) without any inter-GPU traffic.  blocking=False starts the
+        copy on the D2H stream and returns a future (`.wait()`)."""
         local = getattr(self._thunk, "local_block_to_host", None)
         if local is not None:
-            return local(out)
-        return self._thunk.__numpy_array__(out)
+            return local(out, blocking)
+        return self.to_host(out, blocking)
 
     def item(self, *args):
         return self.__array__().item(*args)

@@ -125,10 +125,12 @@ class PartitionedArray:
         return out
 
     @staticmethod
-    def from_local_rows(block: np.ndarray, global_rows: int,
-                        halo: int = DEFAULT_HALO) -> "PartitionedArray":
+    def from_local_rows(block: np.ndarray, global_rows: int, halo: int = DEFAULT_HALO,
+                        blocking: bool = True) -> "PartitionedArray":
         """SPMD upload: `block` holds THIS rank's rows of a (global_rows, ...) array split evenly
-        over the ranks (RowPartition.even) — no rank ever materialises the whole array."""
+        over the ranks (RowPartition.even) — no rank ever materialises the whole array.
+        blocking=False: the copy runs on the H2D stream (pinned source) and overlaps with kernels
+        already queued; the first task that uses the array waits for it."""
         block = np.ascontiguousarray(block)
         out = PartitionedArray.empty((int(global_rows),) + block.shape[1:], block.dtype, halo=halo)
         lo, hi = out.part.bounds(runtime.rank)
@@ -136,15 +138,30 @@ class PartitionedArray:
             raise ValueError(f"rank {runtime.rank} owns rows [{lo}, {hi}) of {global_rows}: expected "
                              f"a block of {hi - lo} rows, got {block.shape[0]}")
         if hi > lo:
-            runtime.copy_h2d(out.local_rows(lo, hi).base.ptr, block)
+            local = out.local_rows(lo, hi).base
+            if blocking:
+                runtime.copy_h2d(local.ptr, block)
+            else:
+                runtime.copy_h2d_async(local.buffer, block, local.offset)
         return out
 
-    def local_block_to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """This rank's rows of the view, copied to the host (no communication)."""
+    def local_block_to_host(self, out: Optional[np.ndarray] = None, blocking: bool = True):
+        """This rank's rows of the view, copied to the host (no communication).  blocking=False
+        returns a future (`.wait()`), the copy runs on the D2H stream."""
         vlo, vhi = self.owned
         if vhi > vlo:
-            return self.local_rows(vlo, vhi).__numpy_array__(out)
-        return np.empty((0,) + self.shape[1:], self.dtype) if out is None else out
+            local = self.local_rows(vlo, vhi)
+            if blocking:
+                return local.__numpy_array__(out)
+            if out is None:
+                out = runtime.pinned_empty(local.shape, local.dtype)
+            return local.to_host_async(out)
+        out = np.empty((0,) + self.shape[1:], self.dtype) if out is None else out
+        if blocking:
+            return out
+        from .deferred import HostFuture
+
+        return HostFuture(None, None, out)
 
     # ------------------------------------------------------------------ properties
     @property

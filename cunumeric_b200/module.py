@@ -103,18 +103,19 @@ def from_host(host: np.ndarray, blocking: bool = True) -> ndarray:
     return ndarray(shape=host.shape, dtype=host.dtype, thunk=DeferredArray.from_numpy_async(host))
 
 
-def from_host_rows(block: np.ndarray, global_rows: int) -> ndarray:
+def from_host_rows(block: np.ndarray, global_rows: int, blocking: bool = True) -> ndarray:
     """SPMD upload of a row-partitioned array: every rank passes ITS block of rows (the even split
-    of `global_rows` over the ranks) — pinned memory is read asynchronously.  With one GPU the block
-    is the whole array."""
+    of `global_rows` over the ranks).  With one GPU the block is the whole array.  blocking=False
+    issues the copy on the H2D stream (pinned source, untouched until the result is first used) so
+    that it overlaps with kernels already queued."""
     block = np.asarray(block)
     if runtime.world_size == 1:
         if block.shape[0] != int(global_rows):
             raise ValueError("single-GPU job: the block must hold every row")
-        return convert_to_cunumeric_ndarray(block)
+        return from_host(block, blocking=blocking)
     from .distributed import PartitionedArray
 
-    thunk = PartitionedArray.from_local_rows(block, global_rows)
+    thunk = PartitionedArray.from_local_rows(block, global_rows, blocking=blocking)
     return ndarray(shape=thunk.shape, dtype=thunk.dtype, thunk=thunk)
 
 

@@ -245,8 +245,8 @@ class Runtime:
     def _recycle_event(self, ev) -> None:
         self._event_pool.append(ev)
 
-    def copy_h2d_async(self, buf: DeviceBuffer, src: np.ndarray) -> None:
-        """Fill `buf` from (pinned) host memory on the H2D stream."""
+    def copy_h2d_async(self, buf: DeviceBuffer, src: np.ndarray, offset: int = 0) -> None:
+        """Fill `buf` (from byte `offset` on) from (pinned) host memory on the H2D stream."""
         assert src.flags.c_contiguous
         h2d, _ = self._copy_streams()
         # the pool handed out `buf` in compute-stream order: do not touch it before that point
@@ -254,7 +254,7 @@ class Runtime:
         _lib.check(self.lib.cnb_event_record(ev, self.stream))
         _lib.check(self.lib.cnb_stream_wait_event(h2d, ev))
         if src.nbytes:
-            _lib.check(self.lib.cnb_memcpy_h2d(buf.ptr, src.ctypes.data, src.nbytes, h2d))
+            _lib.check(self.lib.cnb_memcpy_h2d(buf.ptr + offset, src.ctypes.data, src.nbytes, h2d))
         _lib.check(self.lib.cnb_event_record(ev, h2d))
         buf.ready_event = ev
 

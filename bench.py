@@ -12,6 +12,7 @@ B200" target is quoted on; it fits one GPU, so N = 1 runs the very same job):
                  the cunumeric NumPy API exactly as the reference issues them).
                  metric = interior points updated per second, whole job.
   The same JSON line carries, as extra keys,
+    `c1`             configs[0]: N = 1000 x 100 iterations on one B200 and on ONE host core (N = 1);
     `black_scholes`  configs[1]: examples/black_scholes.py fp32, 1e8 options per GPU (no exchange
                      step: N independent replicas, weak), fused and op-by-op;
     `sweeps`         configs[2] and [4]: the reduction sweep (32768^2 fp32, sum/max/argmax x axis
@@ -595,6 +596,42 @@ def stencil_e2e(args, rank: int, world: int, dist) -> dict:
                    "saturates HBM)"}
 
 
+def c1_leg(args) -> dict:
+    """BASELINE configs[0]: examples/stencil.py fp64 N = 1000, 100 iterations (+5 warm-up, as
+    stencil.py:68-73 does) — the reference's own CPU-runnable case (`legate --cpus 1`), timed on both
+    arms: the product on one B200 (the working set fits L2, the run is bound by the host issuing
+    6 NumPy calls per iteration) and the reference's functors on ONE host core."""
+    import cunumeric_b200 as cn
+    from cunumeric_b200.workloads import stencil_init, stencil_run
+
+    n, iters = 1000, 100
+    grid = stencil_init(n, np.float64)
+    stencil_run(grid, 5)
+    cn.synchronize()
+    t0 = time.perf_counter()
+    stencil_run(grid, iters)
+    cn.synchronize()
+    own = time.perf_counter() - t0
+    out = {"config": "examples/stencil.py fp64 N=1000, 100 iterations (BASELINE configs[0])",
+           "own": {"seconds": own, "points_per_s": float(n) * n * iters / own, "timing": "wall clock "
+                   "around stencil_run + synchronize (host-bound: 0.1 ms of GPU work per iteration)"}}
+    try:
+        from oracle import refnp
+
+        refnp.set_threads(1)
+        g = stencil_init(n, np.float64, xp=refnp)
+        stencil_run(g, 5)
+        t0 = time.perf_counter()
+        stencil_run(g, iters)
+        ref_s = time.perf_counter() - t0
+        out["reference_cpu"] = {"seconds": ref_s, "points_per_s": float(n) * n * iters / ref_s, "cores": 1,
+                                "kind": "reference", "note": "the reference's functors (oracle/_ref) "
+                                "issued op-by-op on one core = `legate --cpus 1`"}
+    except Exception as exc:
+        out["reference_cpu"] = {"unavailable": str(exc)[:200]}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # Black-Scholes (configs[1])
 # ------------------------------------------------------------------------------------------------
@@ -848,6 +885,8 @@ def main() -> None:
                                                         "roofline", "op_by_op", "e2e")}
             cn.runtime.release_cached_memory()
             line["sweeps"] = sweeps_leg(args, rank, world, dist)
+            if world == 1 and not args.no_cpu_baseline:
+                line["c1"] = c1_leg(args)
     else:
         with cn.replicated():
             line = black_scholes_leg(args, rank, world, dist, sampler, primary=True)

@@ -213,3 +213,26 @@ def test_map_reduce_joins_the_chain(sim):
     assert float(m) == max(0.5, (a0 * b0).max()) and np.array_equal(np.array(t), a0 * b0)
     x0, y0 = rng.normal(size=257), rng.normal(size=257)
     assert np.isclose(float(cn.dot(cn.array(x0), cn.array(y0))), np.dot(x0, y0), rtol=1e-12)
+
+
+def test_user_zero_d_arrays_own_their_buffer(sim):
+    """`cn.array(2.0)` must not be a window onto the shared constant cache — an
+    in-place write to it would change what every later `arr * 2.0` reads."""
+    import cunumeric_b200 as cn
+
+    x = cn.array(2.0)
+    assert not x._thunk.base.buffer.shared and x._thunk.host_scalar is None
+    x += 1.0
+    assert float(np.array(x)) == 3.0
+    assert np.array_equal(np.array(cn.array(np.ones(4)) * 2.0), np.full(4, 2.0))
+    y = cn.asarray(np.float64(5.0))
+    y.fill(7.0)
+    assert float(np.array(y)) == 7.0
+    assert np.array_equal(np.array(cn.array(np.ones(3)) * 5.0), np.full(3, 5.0))
+    # +0.0 and -0.0 are different constants (ADVICE r1, medium): the cache key carries the sign
+    from cunumeric_b200._ufunc.ufunc import binary_ufunc
+
+    a = binary_ufunc._weak_scalar(0.0, np.dtype(np.float32))
+    b = binary_ufunc._weak_scalar(-0.0, np.dtype(np.float32))
+    assert a is not b
+    assert not np.signbit(a._thunk.host_scalar) and np.signbit(b._thunk.host_scalar)

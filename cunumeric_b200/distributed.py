@@ -17,6 +17,7 @@ Everything the partition logic decides is a pure function of replicated metadata
 from __future__ import annotations
 
 import ctypes
+import math
 from typing import Any, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -50,37 +51,52 @@ _FOLD_BINOP = {
 }
 
 
+_ALIGN: dict = {}  # (owner tiling, halo, output tiling, first row of the view) -> 0 owned / 1 halo / 2 farther
+_LEAD: dict = {}   # (inner shape, itemsize, halo) -> rows in front of the first owned row
+
+
+def _lead_rows(inner: Tuple[int, ...], itemsize: int, halo: int) -> int:
+    """Rows in front of the first owned row: the ghost rows, padded so that the OWNED block starts on
+    a 128-byte (else 16-byte) boundary — with exactly `halo` rows in front, the local window of a
+    1-D array would start one element into its buffer and every task on it would fall off the
+    128-bit vector path (measured at 2 GPUs: add/bool at 0.17 of the roofline)."""
+    key = (inner, itemsize, halo)
+    lead = _LEAD.get(key)
+    if lead is None:
+        rb = math.prod(inner) * itemsize
+        lead = halo
+        if rb > 0:
+            for unit in (128, 16):
+                need = unit // math.gcd(rb, unit)          # rows per aligned step
+                k = -(-halo // need) * need if halo else 0
+                if k * rb <= max(4096, halo * rb * 8):
+                    lead = int(k)
+                    break
+        if len(_LEAD) > 4096:
+            _LEAD.clear()
+        _LEAD[key] = lead
+    return lead
+
+
 class _Shared:
     """State shared by a base array and all of its views."""
 
     __slots__ = ("gshape", "dtype", "part", "halo", "lead", "local", "ghost_valid", "align_cache")
 
     def __init__(self, gshape, dtype, part: RowPartition, halo: int) -> None:
-        self.gshape = tuple(int(s) for s in gshape)
-        self.dtype = np.dtype(dtype)
+        self.gshape = gshape = tuple(int(s) for s in gshape)
+        self.dtype = dtype = np.dtype(dtype)
         self.part = part
-        self.halo = int(halo)
-        # Rows in front of the first owned row: the ghost rows, padded so that the OWNED block starts on
-        # a 128-byte (else 16-byte) boundary — with exactly `halo` rows in front, the local window of a
-        # 1-D array would start one element into its buffer and every task on it would fall off the
-        # 128-bit vector path (measured at 2 GPUs: add/bool at 0.17 of the roofline).
-        rb = int(np.prod(self.gshape[1:], dtype=np.int64)) * self.dtype.itemsize
-        self.lead = self.halo
-        if rb > 0:
-            for unit in (128, 16):
-                need = unit // np.gcd(rb, unit)          # rows per aligned step
-                k = -(-self.halo // need) * need if self.halo else 0
-                if k * rb <= max(4096, self.halo * rb * 8):
-                    self.lead = int(k)
-                    break
-        rows = part.count(runtime.rank) + self.lead + self.halo
-        self.local = DeferredArray(Store.empty((rows,) + self.gshape[1:], self.dtype))
+        self.halo = halo = int(halo)
+        self.lead = lead = _lead_rows(gshape[1:], dtype.itemsize, halo)
+        rows = part.count(runtime.rank) + lead + halo
+        self.local = DeferredArray(Store.empty((rows,) + gshape[1:], dtype))
         self.ghost_valid = False
         self.align_cache = {}
 
     @property
     def row_bytes(self) -> int:
-        return int(np.prod(self.gshape[1:], dtype=np.int64)) * self.dtype.itemsize
+        return math.prod(self.gshape[1:]) * self.dtype.itemsize
 
 
 def _comm_check(rc: int) -> None:
@@ -227,11 +243,13 @@ class PartitionedArray:
         self.meta.ghost_valid = False
 
     # ------------------------------------------------------------------ exchange
-    def _run_transfers(self, transfers, dst_base_row0: int, dst: DeferredArray) -> None:
+    def _run_transfers(self, transfers, dst_base_row0: int, dst: DeferredArray, stream=None) -> None:
         """Execute a transfer plan in one NCCL group: sends read this rank's block, receives land
         in `dst` (a row-contiguous local buffer whose row 0 is base row `dst_base_row0`)."""
         m = self.meta
-        lib, comm, stream = runtime.lib, runtime.comm, runtime.stream
+        lib, comm = runtime.lib, runtime.comm
+        if stream is None:
+            stream = runtime.stream
         lo, _ = m.part.bounds(runtime.rank)
         rb = m.row_bytes
         mine = [t for t in transfers if t.src == runtime.rank or t.dst == runtime.rank]
@@ -267,16 +285,28 @@ class PartitionedArray:
         # next chain reads, and takes its pointers when it runs — the base buffer may have been
         # renamed by then.  Flushing here instead would launch the previous iteration's chain
         # before its temporaries have died.
-        fusion.enqueue(lambda: self._run_transfers(plan, lo - m.lead, m.local))
+        # The chain in front of it may run AROUND the exchange (fusion.Overlap): the byte ranges tell
+        # it which of its tile rows the exchange depends on.
+        ranges = m.align_cache.get("halo_ranges")
+        if ranges is None:
+            rb, row0 = m.row_bytes, lo - m.lead
+            ranges = m.align_cache["halo_ranges"] = (
+                [((t.row_lo - row0) * rb, (t.row_hi - row0) * rb) for t in plan if t.src == runtime.rank],
+                [((t.row_lo - row0) * rb, (t.row_hi - row0) * rb) for t in plan if t.dst == runtime.rank])
+        overlap = fusion.Overlap(
+            m.local.base.buffer, ranges[0], ranges[1],
+            lambda stream: self._run_transfers(plan, lo - m.lead, m.local, stream))
+        fusion.enqueue(lambda: self._run_transfers(plan, lo - m.lead, m.local), overlap)
         m.ghost_valid = True
 
     def _ensure_aligned_with(self, out_part: RowPartition) -> None:
         """This view is about to be read row for row by a task whose output rows are tiled by
         `out_part`: make the rows every rank needs available (collective).  The classification is a
-        pure function of the two tilings and is cached on the base array."""
+        pure function of the two tilings and is cached (temporaries of a loop body are new arrays with
+        the same tiling every iteration)."""
         m = self.meta
-        key = (out_part, self.row0)
-        kind = m.align_cache.get(key)
+        key = (m.part, m.halo, out_part, self.row0)
+        kind = _ALIGN.get(key)
         if kind is None:
             kind = 0   # 0: owned, 1: within the halo, 2: farther
             for r in range(out_part.world):
@@ -290,7 +320,9 @@ class PartitionedArray:
                     break
                 if nlo < lo or nhi > hi:
                     kind = 1
-            m.align_cache[key] = kind
+            if len(_ALIGN) > 4096:
+                _ALIGN.clear()
+            _ALIGN[key] = kind
         if kind == 1:
             self.exchange_halo()
         elif kind == 2:

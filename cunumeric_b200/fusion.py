@@ -136,12 +136,30 @@ class _Chain:
 
 class _Opaque:
     """A non-elementwise step (e.g. the NCCL halo exchange) that must keep its place in program
-    order between deferred chains.  `fn()` obtains its pointers when it RUNS."""
+    order between deferred chains.  `fn()` obtains its pointers when it RUNS.  `overlap` (optional)
+    describes the step to the chain in front of it, which may then issue it itself — on another
+    stream, between its boundary tiles and its interior tiles (see Overlap)."""
 
-    __slots__ = ("fn",)
+    __slots__ = ("fn", "overlap")
 
-    def __init__(self, fn) -> None:
+    def __init__(self, fn, overlap=None) -> None:
         self.fn = fn
+        self.overlap = overlap
+
+
+class Overlap:
+    """What a queued exchange touches, for the chain that runs right before it: `buffer` is the
+    allocation it works on, `send` / `recv` the byte ranges (relative to the start of the buffer) it
+    reads / writes, `run(stream)` issues it on `stream`.  A chain that writes `buffer` through a
+    renamed, TMA-tiled window launches the tile rows that produce the `send` bytes first, hands the
+    exchange to the communication stream, and computes the interior while the bytes travel; it sets
+    `done` so that the queue does not run the step again."""
+
+    __slots__ = ("buffer", "send", "recv", "run", "done")
+
+    def __init__(self, buffer, send, recv, run) -> None:
+        self.buffer, self.send, self.recv, self.run = buffer, send, recv, run
+        self.done = False
 
 
 _PLAIN_DTYPES = frozenset(np.dtype(t) for t in (
@@ -156,12 +174,13 @@ _chain = _Chain()
 _queue: list = []
 _MAX_SEALED = max(0, int(os.environ.get("CUNUMERIC_B200_FUSION_DEPTH", "1")))
 _RENAME = os.environ.get("CUNUMERIC_B200_RENAME", "1").lower() not in ("0", "off", "false")
+_OVERLAP = os.environ.get("CUNUMERIC_B200_HALO_OVERLAP", "1").lower() not in ("0", "off", "false")
 _flushing = False
 _seen: dict = {}
 _kernels: dict = {}   # signature hash -> (vec kernel, strided kernel, plan class) | None (= unusable)
 stats = {"captured": 0, "fused_launches": 0, "fused_tasks": 0, "replayed_tasks": 0,
          "elided_tasks": 0, "compiled": 0, "renamed": 0, "deferred": 0, "tma_launches": 0,
-         "fused_reductions": 0, "tma_refused": 0}
+         "fused_reductions": 0, "tma_refused": 0, "overlapped_exchanges": 0}
 
 
 _rt: list = []
@@ -375,7 +394,7 @@ def seal() -> None:
     _drain(_MAX_SEALED)
 
 
-def enqueue(fn) -> None:
+def enqueue(fn, overlap: Optional[Overlap] = None) -> None:
     """Run `fn()` in program order with respect to the deferred chains: right away if nothing is
     pending, else after everything captured so far (and before everything captured later)."""
     if _flushing or not pending():
@@ -385,7 +404,7 @@ def enqueue(fn) -> None:
     if not _queue:
         fn()
         return
-    _queue.append(_Opaque(fn))
+    _queue.append(_Opaque(fn, overlap if _OVERLAP else None))
 
 
 def flush() -> None:
@@ -413,9 +432,11 @@ def _drain(keep: int) -> None:
                 break
             step = _queue.pop(0)
             if isinstance(step, _Opaque):
-                step.fn()
+                if step.overlap is None or not step.overlap.done:
+                    step.fn()
             else:
-                _run_chain(step)
+                nxt = _queue[0] if _queue else None
+                _run_chain(step, nxt.overlap if isinstance(nxt, _Opaque) else None)
     finally:
         _flushing = False
 
@@ -453,7 +474,7 @@ def _rename_geometry(c: _Chain, w: _Window):
 _plan_memo: dict = {}   # structural key of a chain -> (entry, n_keep, output value ids, input value ids)
 
 
-def _run_chain(c: _Chain) -> None:
+def _run_chain(c: _Chain, overlap: Optional[Overlap] = None) -> None:
     runtime = _rt[0] if _rt else _get_runtime()
     # this chain's own reads are resolved by this launch: what remains in `readers` are the reads
     # of YOUNGER pending chains
@@ -477,7 +498,7 @@ def _run_chain(c: _Chain) -> None:
         by_vid = {vid: w for vid, w in live}
         stats["elided_tasks"] += len(c.tasks) - n_keep
         if _launch(entry, c.shape, [by_vid[v] for v in out_vids], [c.ext[v] for v in in_vids],
-                   n_keep, c.renamed):
+                   n_keep, c.renamed, overlap=overlap):
             return
     needed = set(v for v, _ in live)
     keep: List[_Task] = []
@@ -527,7 +548,7 @@ def _run_chain(c: _Chain) -> None:
     if len(_plan_memo) > 4096:
         _plan_memo.clear()
     _plan_memo[memo_key] = (entry, len(keep), [v for _, v, _ in out_pairs], in_vids)
-    if not _launch(entry, c.shape, out_windows, in_windows, len(keep), c.renamed):
+    if not _launch(entry, c.shape, out_windows, in_windows, len(keep), c.renamed, overlap=overlap):
         _replay(c, keep)
 
 
@@ -581,7 +602,7 @@ def _replay(c: _Chain, tasks: List[_Task]) -> None:
 # ---------------------------------------------------------------------------------------------
 # kernel lookup / generation / compilation
 # ---------------------------------------------------------------------------------------------
-_GENERATOR_VERSION = 11
+_GENERATOR_VERSION = 12
 _src_tag: List[str] = []
 
 
@@ -1146,7 +1167,8 @@ def generate_tma_source(sig, lay, h: str) -> str:
              f"STAGE = {geo['stage']}, TX_BYTES = {geo['tx_bytes']}, NG = {ng};")
     L.append("struct alignas(64) TMap { unsigned char bytes[128]; };")
     L.append("struct TOut { char* ptr; long long row_stride; };")
-    L.append("struct TParams {\n  TMap maps[NG];\n  long long inner, rows;\n  int tiles_x, num_tiles, cshift, pad_;\n"
+    L.append("struct TParams {\n  TMap maps[NG];\n  long long inner, rows;\n"
+             "  int tiles_x, num_tiles, cshift, ty_split, ty_skip, pad_;\n"
              "  int gx[NG], gy[NG], gshift[NG];\n"
              f"  TOut out[{n_out}];\n  const char* scalar[{max(1, len(scalars))}];\n"
              "  unsigned int* sched;   // {next tile, finished CTAs}: filled in by cnb_launch_fused_tma\n};")
@@ -1178,7 +1200,9 @@ def generate_tma_source(sig, lay, h: str) -> str:
     const int t = (int)atomicAdd(P.sched, 1u);
     tile_ring[k & 15] = t;
     if (t < P.num_tiles) {
-      const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+      int ty = t / P.tiles_x;
+      const int tx = t - ty * P.tiles_x;
+      if (ty >= P.ty_split) ty += P.ty_skip;   // a launch over a subset of the tile rows (see _launch_tma)
       const int s = k % S;
       const uint32_t bar = smem_u32(&full[s]);
       mbar_arrive_expect_tx(bar, TX_BYTES);""")
@@ -1196,7 +1220,9 @@ def generate_tma_source(sig, lay, h: str) -> str:
     L.append("""  for (int k = 0;; ++k) {
     const int t = tile_ring[k & 15];
     if (t >= P.num_tiles) break;
-    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+    int ty = t / P.tiles_x;
+    const int tx = t - ty * P.tiles_x;
+    if (ty >= P.ty_split) ty += P.ty_skip;
     const int s = k % S;
     mbar_wait(smem_u32(&full[s]), (k / S) & 1);""")
     # gather: every (row, column) offset of every group some row of this thread needs
@@ -1248,7 +1274,8 @@ def _tma_params_type(ng: int, n_out: int, n_scalar: int):
     class Tail(ctypes.Structure):
         _fields_ = [("inner", ctypes.c_int64), ("rows", ctypes.c_int64),
                     ("tiles_x", ctypes.c_int32), ("num_tiles", ctypes.c_int32),
-                    ("cshift", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                    ("cshift", ctypes.c_int32), ("ty_split", ctypes.c_int32),
+                    ("ty_skip", ctypes.c_int32), ("pad_", ctypes.c_int32),
                     ("gx", ctypes.c_int32 * ng), ("gy", ctypes.c_int32 * ng),
                     ("gshift", ctypes.c_int32 * ng),
                     ("out", TOut * n_out), ("scalar", ctypes.c_void_p * max(1, n_scalar)),
@@ -1293,8 +1320,49 @@ def _lookup_tma(sig, lay):
     return entry
 
 
+def _overlap_split(ov: Overlap, out_windows, renamed, inner: int, rows: int, row_st, tiles_y: int):
+    """(top, bottom) tile rows that must run before the exchange `ov` may start, or None if the chain
+    cannot run around it.  The chain has to write ov.buffer through its renamed window only: then its
+    reads of that buffer go to the OLD block, which the exchange does not touch, and the tile rows
+    that write none of the exchanged bytes are independent of the exchange."""
+    buf = ov.buffer
+    geo = renamed.get(id(buf)) if renamed else None
+    if geo is None:
+        return None
+    top = bot = 0
+    found = False
+    for k, w in enumerate(out_windows):
+        if w.buffer is not buf:
+            continue
+        rs = row_st[k]
+        if geo[0].key != w.key or rs <= 0 or found:
+            return None
+        found = True
+        row_bytes = inner * w.dtype.itemsize
+        for lo, hi in list(ov.send) + list(ov.recv):
+            # window rows r with [offset + r rs, offset + r rs + row_bytes) intersecting [lo, hi)
+            first = max(0, -(-(lo - w.offset - row_bytes + 1) // rs))
+            last = min(rows - 1, (hi - 1 - w.offset) // rs)
+            if first > last:
+                continue
+            if last + 1 <= rows - first:
+                top = max(top, last + 1)
+            else:
+                bot = max(bot, rows - first)
+    if not found:
+        return None
+    nt, nb = -(-top // TMA_TR), -(-bot // TMA_TR)
+    if nt + nb == 0 or (nt + nb) * 4 > tiles_y:
+        return None
+    return nt, nb
+
+
 def _launch_tma(sig, lay, groups, inner, rows, row_st, out_windows, in_windows, ptrs, algo,
-                ntasks: int) -> bool:
+                ntasks: int, commit, renamed=None, overlap: Optional[Overlap] = None) -> bool:
+    """Launch the TMA flavour and commit the renamed blocks.  With an exchange to overlap: the tile
+    rows that produce the bytes the exchange sends run first; the exchange is then issued on the
+    communication stream, and the interior tile rows on the compute stream next to it; the compute
+    stream waits for the exchange at the end."""
     from .runtime import runtime
 
     entry = _lookup_tma(sig, lay)
@@ -1327,7 +1395,6 @@ def _launch_tma(sig, lay, groups, inner, rows, row_st, out_windows, in_windows, 
     tiles_y = -(-rows // TMA_TR)
     if tiles_x * tiles_y >= 2 ** 31 - 2 ** 20:
         return False
-    tail.tiles_x, tail.num_tiles = tiles_x, tiles_x * tiles_y
     for k in range(n_out):
         tail.out[k].ptr = ptrs[k]
         tail.out[k].row_stride = row_st[k]
@@ -1336,13 +1403,45 @@ def _launch_tma(sig, lay, groups, inner, rows, row_st, out_windows, in_windows, 
         if e is None:
             tail.scalar[n] = ptrs[n_out + i]
             n += 1
-    rc = runtime.lib.cnb_launch_fused_tma(kern, ops, ng, ctypes.byref(tail), ctypes.sizeof(tail),
-                                          geo["smem"], tail.num_tiles, inner * rows, algo, ntasks, 2,
-                                          runtime.stream)
+    tail.tiles_x = tiles_x
+    lib = runtime.lib
+
+    def launch(count: int, skip_at: int, skip: int) -> int:
+        """`count` tile rows: launch row y is tile row y, or y + skip from launch row `skip_at` on."""
+        tail.ty_split, tail.ty_skip = skip_at, skip
+        tail.num_tiles = tiles_x * count
+        share = count / tiles_y
+        return lib.cnb_launch_fused_tma(kern, ops, ng, ctypes.byref(tail), ctypes.sizeof(tail),
+                                        geo["smem"], tail.num_tiles, int(inner * rows * share),
+                                        int(algo * share), ntasks, 2, runtime.stream)
+
+    split = None
+    if overlap is not None and not overlap.done:
+        split = _overlap_split(overlap, out_windows, renamed, inner, rows, row_st, tiles_y)
+    if split is None:
+        rc = launch(tiles_y, tiles_y, 0)
+    else:
+        nt, nb = split
+        # boundary: tile rows [0, nt) and [tiles_y - nb, tiles_y)
+        rc = launch(nt + nb, nt, tiles_y - nt - nb)
     if rc == -4:     # CNB_ERR_UNSUPPORTED: the driver refused a tensor map — the strided flavour serves
         stats["tma_refused"] += 1
         return False
     _lib.check(rc)
+    commit()         # the exchange below takes the pointers of the adopted blocks
+    if split is not None:
+        comm_stream = runtime.comm_stream()
+        ev = runtime._event()
+        _lib.check(lib.cnb_event_record(ev, runtime.stream))
+        _lib.check(lib.cnb_stream_wait_event(comm_stream, ev))
+        overlap.run(comm_stream)
+        overlap.done = True
+        _lib.check(lib.cnb_event_record(ev, comm_stream))
+        # interior: tile rows [nt, tiles_y - nb)
+        _lib.check(launch(tiles_y - nt - nb, 0, nt))
+        _lib.check(lib.cnb_stream_wait_event(runtime.stream, ev))
+        runtime._recycle_event(ev)
+        stats["overlapped_exchanges"] += 1
     return True
 
 
@@ -1436,7 +1535,8 @@ def _distinct_bytes(windows, dims_of, renamed=None, n_out: int = 0) -> int:
     return total
 
 
-def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dry: bool = False) -> bool:
+def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dry: bool = False,
+            overlap: Optional[Overlap] = None) -> bool:
     """Pick the kernel flavour for this layout (128-bit vector / TMA-staged tiles / strided) and
     launch it.  `dry`: only make sure the kernels the layout needs are compiled (trace_only)."""
     from .runtime import runtime
@@ -1481,8 +1581,7 @@ def _launch(entry, shape, out_windows, in_windows, ntasks: int, renamed=None, dr
         windows, lambda k: (inner if inner_st[k] != 0 else 1) * (rows if row_st[k] != 0 else 1),
         renamed, n_out)
     if tma is not None and _launch_tma(sig, tma[0], tma[1], inner, rows, row_st, out_windows,
-                                       in_windows, ptrs, algo, ntasks):
-        commit()
+                                       in_windows, ptrs, algo, ntasks, commit, renamed, overlap):
         stats["fused_launches"] += 1
         stats["fused_tasks"] += ntasks
         stats["tma_launches"] += 1

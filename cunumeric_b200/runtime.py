@@ -108,6 +108,7 @@ class Runtime:
         self._argred_uids: dict = {}
         self._h2d_stream: Any = None
         self._d2h_stream: Any = None
+        self._comm_stream: Any = None
         self._event_pool: list = []
         self._free_blocks: dict = {}
         self._cached_bytes = 0
@@ -237,6 +238,13 @@ class Runtime:
             self._h2d_stream = _lib.check_ptr(self.lib.cnb_stream_create())
             self._d2h_stream = _lib.check_ptr(self.lib.cnb_stream_create())
         return self._h2d_stream, self._d2h_stream
+
+    def comm_stream(self):
+        """Stream of the halo exchanges that run next to the interior tiles of a fused chain
+        (fusion._launch_tma); ordered with the compute stream by events only."""
+        if self._comm_stream is None:
+            self._comm_stream = _lib.check_ptr(self.lib.cnb_stream_create())
+        return self._comm_stream
 
     def _event(self):
         return self._event_pool.pop() if self._event_pool else _lib.check_ptr(

@@ -38,6 +38,7 @@ def main() -> None:
 
     for n, iters, dt in ((254, 6, np.float64), (1022, 5, np.float64), (510, 4, np.float32)):
         before = fusion.stats["tma_launches"]
+        overlapped = fusion.stats["overlapped_exchanges"]
         g = stencil_init(n, dt, xp=cn)
         w = stencil_run(g, iters)
         g_np = stencil_init(n, dt, xp=np)
@@ -46,6 +47,10 @@ def main() -> None:
         assert np.array_equal(g.__array__(), g_np), f"stencil grid mismatch n={n}"
         if fusion.enabled() and n // world >= 16:
             assert fusion.stats["tma_launches"] - before >= iters, (n, fusion.stats)
+        if fusion.enabled() and fusion._OVERLAP and n // world >= 8 * fusion.TMA_TR + 2:
+            # enough tile rows per rank: the halo exchange of every iteration but the last ran on the
+            # communication stream between the boundary and the interior tiles of the chain before it
+            assert fusion.stats["overlapped_exchanges"] - overlapped >= iters - 1, (n, fusion.stats)
 
     # ---- elementwise on partitioned + replicated operands
     rng = np.random.default_rng(5)

@@ -181,7 +181,7 @@ def make_fused_launcher(lib: SimLib, schedule_rng=None):
                 vals[out] = np.asarray(r, dtype=DTYPES[code])
         return vals
 
-    def launch(entry, shape, out_windows, in_windows, ntasks, renamed=None):
+    def launch(entry, shape, out_windows, in_windows, ntasks, renamed=None, dry=False, overlap=None):
         from cunumeric_b200 import fusion
 
         _, sig = entry
@@ -191,6 +191,40 @@ def make_fused_launcher(lib: SimLib, schedule_rng=None):
         n_out = len(out_windows)
         outs_v = [window_view(w, p) for w, p in zip(out_windows, ptrs[:n_out])]
         ins_v = [window_view(w, p) for w, p in zip(in_windows, ptrs[n_out:])]
+
+        def run_rows(rows):
+            for i in rows:
+                vals = evaluate(sig, {k: v[i:i + 1].copy() for k, v in enumerate(ins_v)})
+                pairs = list(zip(outs, outs_v))
+                for (v, code), o in (reversed(pairs) if i % 2 else pairs):
+                    o[i:i + 1] = vals[v]
+
+        # a queued exchange the chain may run around (fusion.Overlap), decided by the product's own
+        # dependence analysis: boundary tile rows, then the exchange, then the interior
+        split = None
+        if overlap is not None and not overlap.done and len(shape) == 2 and \
+                not any(t[0] == "R" for t in sig[1]):
+            windows = list(out_windows) + list(in_windows)
+            dims = fusion._canonical(shape, [w.strides for w in windows])
+            if len(dims) == 2 and dims[0][0] == shape[0]:
+                rows, row_st = dims[0]
+                tiles_y = -(-rows // fusion.TMA_TR)
+                split = fusion._overlap_split(overlap, out_windows, renamed, dims[1][0], rows, row_st,
+                                              tiles_y)
+        if split is not None:
+            nt, nb = split
+            top, bot = nt * fusion.TMA_TR, shape[0] - nb * fusion.TMA_TR
+            assert 0 < top <= bot < shape[0] or nt == 0 or nb == 0
+            run_rows(list(range(0, top)) + list(range(bot, shape[0])))
+            commit()
+            overlap.run(None)
+            overlap.done = True
+            fusion.stats["overlapped_exchanges"] += 1
+            run_rows(range(bot - 1, top - 1, -1))
+            lib.stored_outputs = getattr(lib, "stored_outputs", []) + [len(out_windows)]
+            lib.launches += 1
+            lib.fused_launches += 1
+            return True
         mode = int(rng.integers(3)) if len(shape) >= 1 and shape[0] > 1 else 0
         if any(t[0] == "R" for t in sig[1]):
             mode = 0   # a reduction spans the rows: evaluate the chain in one piece

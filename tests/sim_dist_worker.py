@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ["CUNUMERIC_B200_MIN_PARTITION"] = "1"
+os.environ.setdefault("CNB_TMA_TR", "4")   # tile rows of 4: small grids still have interior tile rows
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -74,7 +75,7 @@ def main() -> None:
     mode = os.environ.get("SIM_FUSION", "always")
     fusion._mode = mode
 
-    for n, iters in ((30, 3), (13, 5), (64, 4)):
+    for n, iters in ((30, 3), (13, 5), (64, 4), (130, 6)):
         g = stencil_init(n, np.float64, xp=cn)
         assert isinstance(g._thunk, PartitionedArray)
         w = stencil_run(g, iters)
@@ -85,6 +86,10 @@ def main() -> None:
             f"{np.argwhere(got_g != g_np)[:4].tolist()}"
         assert np.array_equal(got_w, w_np), f"rank {rank}: work mismatch n={n} mode={mode}: " \
             f"{np.argwhere(got_w != w_np)[:4].tolist()}"
+    if mode == "always" and fusion._OVERLAP and fusion._RENAME and fusion._MAX_SEALED >= 1:
+        # the n=130 grid has enough tile rows per rank: its halo exchanges ran BETWEEN the boundary
+        # and the interior rows of the chain in front of them (fusion.Overlap)
+        assert fusion.stats["overlapped_exchanges"] >= 4, fusion.stats
     # a second program: elementwise on shifted row views of a partitioned array, in-place update
     rng = np.random.default_rng(3)
     a0 = rng.normal(size=(41, 7))

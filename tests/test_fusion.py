@@ -140,7 +140,7 @@ def _dry(prog):
     _dry.renames = []
     orig = fusion._run_chain
 
-    def spy(c):
+    def spy(c, overlap=None):
         live = sum(1 for _, w in c.written.values() if w.buffer.users > 0)
         flushed.append(([t.kind + str(t.op) for t in c.tasks], live))
         _dry.renames.append((len(c.tasks), live, len(c.renamed)))

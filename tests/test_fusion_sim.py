@@ -236,3 +236,39 @@ def test_user_zero_d_arrays_own_their_buffer(sim):
     b = binary_ufunc._weak_scalar(-0.0, np.dtype(np.float32))
     assert a is not b
     assert not np.signbit(a._thunk.host_scalar) and np.signbit(b._thunk.host_scalar)
+
+
+def test_overlap_split_dependence_analysis(sim):
+    """fusion._overlap_split: which tile rows of a chain a queued halo exchange depends on."""
+    from cunumeric_b200 import fusion
+    from cunumeric_b200.store import Store
+
+    tr = fusion.TMA_TR
+    rows, cols, item = 40 * tr + 2, 64, 8          # local block: 1 ghost row + owned rows + 1 ghost row
+    pitch = cols * item
+    buf = Store.empty((rows, cols), np.float64)
+    centre = buf.slice(0, slice(1, rows - 1)).slice(1, slice(1, cols - 1))
+    w = fusion._Window(centre)
+    geo = {id(buf.buffer): (w, w.offset, rows - 2, (cols - 2) * item, pitch)}
+    send = [(1 * pitch, 2 * pitch), ((rows - 2) * pitch, (rows - 1) * pitch)]
+    recv = [(0, pitch), ((rows - 1) * pitch, rows * pitch)]
+    ov = fusion.Overlap(buf.buffer, send, recv, lambda stream: None)
+    tiles_y = -(-(rows - 2) // tr)
+    args = (cols - 2, rows - 2, [pitch], tiles_y)
+    assert fusion._overlap_split(ov, [w], geo, *args) == (1, 1)
+    # a halo of tr + 1 rows reaches into the second tile row
+    deep = fusion.Overlap(buf.buffer, [(pitch, (tr + 2) * pitch)], [], lambda stream: None)
+    assert fusion._overlap_split(deep, [w], geo, *args) == (2, 0)
+    # not renamed: the chain's reads and the exchange's writes share a block
+    assert fusion._overlap_split(ov, [w], None, *args) is None
+    assert fusion._overlap_split(ov, [w], {}, *args) is None
+    # the chain does not write the exchanged buffer / writes it through another window as well
+    other = fusion._Window(Store.empty((rows - 2, cols - 2), np.float64))
+    assert fusion._overlap_split(ov, [other], geo, *args) is None
+    w2 = fusion._Window(buf.slice(0, slice(0, rows - 2)).slice(1, slice(0, cols - 2)))
+    assert fusion._overlap_split(ov, [w, w2], geo, cols - 2, rows - 2, [pitch, pitch], tiles_y) is None
+    # too few tile rows for an interior worth the extra launch
+    assert fusion._overlap_split(ov, [w], geo, cols - 2, rows - 2, [pitch], 4) is None
+    # an exchange that touches none of the written rows does not depend on the chain
+    far = fusion.Overlap(buf.buffer, [], [(0, pitch)], lambda stream: None)
+    assert fusion._overlap_split(far, [w], geo, *args) is None

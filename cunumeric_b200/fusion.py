@@ -174,7 +174,11 @@ _chain = _Chain()
 _queue: list = []
 _MAX_SEALED = max(0, int(os.environ.get("CUNUMERIC_B200_FUSION_DEPTH", "1")))
 _RENAME = os.environ.get("CUNUMERIC_B200_RENAME", "1").lower() not in ("0", "off", "false")
-_OVERLAP = os.environ.get("CUNUMERIC_B200_HALO_OVERLAP", "1").lower() not in ("0", "off", "false")
+# Halo exchange next to the interior tiles of the chain in front of it (Overlap): OFF by default.
+# Measured at 8 GPUs (profiles/r02_scaling.md): 0.529 ms / iteration with it, 0.519 without — the
+# persistent interior kernel fills every SM before the NCCL kernel of the other stream is placed, so
+# the exchange still runs after it and the extra boundary launch is pure cost.
+_OVERLAP = os.environ.get("CUNUMERIC_B200_HALO_OVERLAP", "0").lower() in ("1", "on", "true")
 _flushing = False
 _seen: dict = {}
 _kernels: dict = {}   # signature hash -> (vec kernel, strided kernel, plan class) | None (= unusable)

@@ -8,6 +8,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["CUNUMERIC_B200_MIN_PARTITION"] = "1"
+os.environ.setdefault("CUNUMERIC_B200_HALO_OVERLAP", "1")   # opt-in path (fusion.Overlap): covered here
 
 import torch.distributed as dist  # noqa: E402
 

@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ["CUNUMERIC_B200_MIN_PARTITION"] = "1"
+os.environ.setdefault("CUNUMERIC_B200_HALO_OVERLAP", "1")   # opt-in path (fusion.Overlap): covered here
 os.environ.setdefault("CNB_TMA_TR", "4")   # tile rows of 4: small grids still have interior tile rows
 
 import torch  # noqa: E402

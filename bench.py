@@ -480,6 +480,14 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
         stencil_run(grid, iters)
         cn.flush()
     cn.synchronize()
+    # host cost of issuing one iteration with an EMPTY launch queue (20 iterations are ~60 launches, far
+    # below the depth at which the driver blocks the issuing thread); the figure taken inside the timed
+    # region below includes the time the host spends blocked behind a full queue
+    t_free = time.perf_counter()
+    stencil_run(grid, 20)
+    cn.flush()
+    t_free = (time.perf_counter() - t_free) / 20
+    cn.synchronize()
 
     _lib.check(lib.cnb_trace_start(steps * iters * (STENCIL_TASKS_PER_ITER + 3) + 16))
     timer = DeviceTimer(cn, dist)
@@ -528,6 +536,10 @@ def stencil_leg(args, rank: int, world: int, dist, sampler) -> dict:
                    "execution": "fused" if fused_on else "op-by-op",
                    "N": n, "iters_per_step": iters, "ms_per_iteration": 1e3 * elapsed / steps / iters,
                    "host_issue_ms_per_iteration": 1e3 * t_issue / steps / iters,
+                   "host_issue_ms_per_iteration_empty_queue": 1e3 * t_free,
+                   "host_issue_note": "the first figure is taken inside the timed region and includes "
+                                      "the time the issuing thread is blocked behind a full launch queue "
+                                      "(it tracks the GPU time); the second is the host's own cost",
                    "algorithmic_bytes_per_point": round(bytes_per_point, 3),
                    "collective": ("ncclSend/ncclRecv of one ghost row per neighbour per iteration "
                                   "(grouped, stream-ordered)" if world > 1 else "none (1 GPU)"),

@@ -18,6 +18,15 @@ from .runtime import runtime
 from .store import Store
 
 
+# reductions that can run one axis at a time -> the op that continues over the partial results
+_SEPARABLE_REDS = {
+    UnaryRedCode.SUM: UnaryRedCode.SUM, UnaryRedCode.PROD: UnaryRedCode.PROD,
+    UnaryRedCode.MAX: UnaryRedCode.MAX, UnaryRedCode.MIN: UnaryRedCode.MIN,
+    UnaryRedCode.ALL: UnaryRedCode.ALL, UnaryRedCode.ANY: UnaryRedCode.ANY,
+    UnaryRedCode.COUNT_NONZERO: UnaryRedCode.SUM,
+}
+
+
 def _normalize_axis_tuple(axis, ndim: int) -> tuple:
     if isinstance(axis, (int, np.integer)):
         axis = (int(axis),)
@@ -550,6 +559,34 @@ class ndarray:
                 out_shape += (src.shape[dim],)
             elif keepdims:
                 out_shape += (1,)
+        if 1 < len(axes) < src.ndim and op in _SEPARABLE_REDS and not args and \
+                type(src._thunk) is DeferredArray:
+            # Several (not all) axes.  The reference stops here (deferred.py:3259-3262 "Need support
+            # for reducing multiple dimensions"); these reductions are separable, so they run as one
+            # UNARY_RED per axis, innermost first: `where` applies to the first pass, `initial`
+            # joins the last one, and COUNT_NONZERO continues as a SUM of the counts.
+            cur = src
+            order = sorted(axes, reverse=True)
+            for i, ax in enumerate(order):
+                first, last = i == 0, i == len(order) - 1
+                if first:
+                    cur = cls._perform_unary_reduction(
+                        op, cur, axis=ax, keepdims=True, where=where,
+                        initial=initial if last else None,
+                        **({"res_dtype": res_dtype} if dtype == src.dtype and res_dtype != dtype
+                           else {"dtype": dtype}))
+                else:
+                    cur = cls._perform_unary_reduction(
+                        _SEPARABLE_REDS[op], cur, axis=ax, keepdims=True, res_dtype=cur.dtype,
+                        initial=initial if last else None)
+            cur = cur.reshape(out_shape)
+            if out is None:
+                return cur
+            if out.shape != out_shape:
+                raise ValueError(f"the output shapes do not match: expected {out_shape} but got "
+                                 f"{out.shape}")
+            out._thunk.convert(cur._thunk)
+            return out
         if out is None:
             out = ndarray(shape=out_shape, dtype=res_dtype, inputs=(src, where))
         elif out.shape != out_shape:

@@ -140,6 +140,37 @@ class SimLib:
         self.launches += 1
         return 0
 
+    # ---- reductions (reduce-accessor semantics: fold into the pre-filled output)
+    _AXIS_RED = {
+        int(UnaryRedCode.SUM): (np.add, lambda x, ax: x.sum(axis=ax, dtype=x.dtype)),
+        int(UnaryRedCode.PROD): (np.multiply, lambda x, ax: x.prod(axis=ax, dtype=x.dtype)),
+        int(UnaryRedCode.MAX): (np.maximum, lambda x, ax: x.max(axis=ax)),
+        int(UnaryRedCode.MIN): (np.minimum, lambda x, ax: x.min(axis=ax)),
+        int(UnaryRedCode.ALL): (np.logical_and, lambda x, ax: x.all(axis=ax)),
+        int(UnaryRedCode.ANY): (np.logical_or, lambda x, ax: x.any(axis=ax)),
+        int(UnaryRedCode.COUNT_NONZERO): (np.add, lambda x, ax: np.count_nonzero(x, axis=ax)),
+    }
+
+    def cnb_unary_red(self, op, axis, out, inp, where, flags, stream):
+        assert where is None, "the stand-in has no masked reductions"
+        fold, red = self._AXIS_RED[op]
+        o, a = _desc_view(out), _desc_view(inp)
+        first = [slice(None)] * o.ndim
+        first[axis] = slice(0, 1)                 # the output is promoted (stride 0) along the axis
+        target = o[tuple(first)]
+        part = np.expand_dims(red(a.copy(), axis), axis)
+        target[...] = fold(target.copy(), part).astype(o.dtype)
+        self.launches += 1
+        return 0
+
+    def cnb_scalar_unary_red(self, op, out, inp, where, origin, gshape, extra, stream):
+        assert where is None and extra is None
+        fold, red = self._AXIS_RED[op]
+        o, a = _desc_view(out), _desc_view(inp)
+        o[...] = fold(o.copy(), red(a.copy(), None)).astype(o.dtype)
+        self.launches += 1
+        return 0
+
     def cnb_convert(self, nan_op, out, inp, stream):
         o = _desc_view(out)
         o[...] = _desc_view(inp).copy().astype(o.dtype)

@@ -272,3 +272,37 @@ def test_overlap_split_dependence_analysis(sim):
     # an exchange that touches none of the written rows does not depend on the chain
     far = fusion.Overlap(buf.buffer, [], [(0, pitch)], lambda stream: None)
     assert fusion._overlap_split(far, [w], geo, *args) is None
+
+
+def test_multi_axis_reductions_run_axis_by_axis(sim):
+    """sum / prod / max / min / all / any / count_nonzero over SEVERAL axes (the reference raises
+    NotImplementedError, deferred.py:3259-3262): one UNARY_RED per axis, innermost first."""
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(11)
+    a = rng.integers(-4, 5, size=(3, 4, 5, 6)).astype(np.int64)
+    A = cn.array(a)
+    for axes in ((0, 1), (1, 3), (0, 2, 3), (-1, 0), (2, 1)):
+        for keepdims in (False, True):
+            assert np.array_equal(A.sum(axis=axes, keepdims=keepdims).__array__(),
+                                  a.sum(axis=axes, keepdims=keepdims))
+            assert np.array_equal(A.max(axis=axes, keepdims=keepdims).__array__(),
+                                  a.max(axis=axes, keepdims=keepdims))
+            assert np.array_equal(A.min(axis=axes, keepdims=keepdims).__array__(),
+                                  a.min(axis=axes, keepdims=keepdims))
+        assert np.array_equal(A.prod(axis=axes).__array__(), a.prod(axis=axes))
+        assert np.array_equal((A > 0).all(axis=axes).__array__(), (a > 0).all(axis=axes))
+        assert np.array_equal((A > 3).any(axis=axes).__array__(), (a > 3).any(axis=axes))
+        assert np.array_equal(cn.count_nonzero(A, axis=axes).__array__(), np.count_nonzero(a, axis=axes))
+    assert np.array_equal(A.sum(axis=(0, 2), initial=7).__array__(), a.sum(axis=(0, 2), initial=7))
+    assert np.array_equal(A.sum(axis=(1, 2), dtype=np.float64).__array__(),
+                          a.sum(axis=(1, 2), dtype=np.float64))
+    out = cn.empty((3, 6), dtype=np.int64)
+    assert A.sum(axis=(1, 2), out=out) is out
+    assert np.array_equal(out.__array__(), a.sum(axis=(1, 2)))
+    with pytest.raises(ValueError):
+        A.sum(axis=(1, 2), out=cn.empty((3, 5), dtype=np.int64))
+    with pytest.raises(ValueError):
+        A.sum(axis=(1, 1))
+    # all axes named explicitly: the scalar reduction, as before
+    assert int(A.sum(axis=(0, 1, 2, 3))) == int(a.sum())

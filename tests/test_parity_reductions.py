@@ -351,3 +351,39 @@ def test_few_very_long_rows_are_split_across_ctas(op, shape, dt):
         exp = ref.unary_red(op, a, axis)
     got = thunk_reduce(op, a, axis=axis)
     check_reduction(op, a, got, exp, shape[-1], f"{op}/{dt.name}/{shape}")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.uint8], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("shape,axes", [((5, 7, 9), (0, 2)), ((5, 7, 9), (1, 2)), ((3, 4, 5, 6), (0, 1, 3)),
+                                        ((64, 33, 130), (0, 1)), ((2, 300, 2, 70), (1, 3))])
+def test_multi_axis_reductions(shape, axes, dt):
+    """Several axes at once (ndarray._perform_unary_reduction; the reference raises,
+    deferred.py:3259-3262): one UNARY_RED per axis, innermost first.  Expected = the oracle's UNARY_RED
+    applied in the same order; exact for integers / MAX / MIN, n * eps for floating sums."""
+    import cunumeric_b200 as cn
+
+    dt = np.dtype(dt)
+    rng = pu.rng_for("multi-axis", dt.name, shape, axes)
+    a = red_input("SUM", dt, shape, rng)
+    A = cn.array(a)
+    n = int(np.prod([shape[x] for x in axes]))
+
+    def oracle(op, follow):
+        cur = a
+        for i, ax in enumerate(sorted(axes, reverse=True)):
+            cur = ref.unary_red(op if i == 0 else follow, cur, ax)
+        return cur
+
+    for op, fn in (("MAX", lambda x: x.max(axis=axes)), ("MIN", lambda x: x.min(axis=axes))):
+        assert np.array_equal(fn(A).__array__(), oracle(op, op)), op
+    got, exp = A.sum(axis=axes).__array__(), oracle("SUM", "SUM")
+    assert got.dtype == exp.dtype and got.shape == exp.shape
+    if dt.kind in "iu":
+        assert np.array_equal(got, exp)
+    else:
+        bound = n * np.finfo(dt).eps * np.abs(a).sum(axis=axes, dtype=np.float64)
+        assert np.all(np.abs(got.astype(np.float64) - exp.astype(np.float64)) <= bound)
+    assert np.array_equal(cn.count_nonzero(A, axis=axes).__array__(),
+                          np.count_nonzero(a, axis=axes))
+    assert np.array_equal(A.sum(axis=axes, keepdims=True).__array__().shape,
+                          a.sum(axis=axes, keepdims=True).shape)

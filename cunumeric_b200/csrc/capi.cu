@@ -245,6 +245,160 @@ int try_split_long_rows(int op, int axis, const cnb_store_t* out, const cnb_stor
   pool_free(scratch, s);
   return rc;
 }
+
+// ---- pitched views that start off a 16-byte boundary ---------------------------------------------
+// `x[1:-1, 1:-1].sum(...)`: the rows keep a 16-byte-multiple pitch, but every row starts (and ends)
+// inside a 16-byte word, so the whole task falls off the vector / bulk-copy kernels onto the
+// element-wise ones (measured on 16382 x 16382 fp32: axis 0 at 0.34, axis 1 at 0.75, full at 0.49 of
+// the HBM peak).  The contiguous dim is cut into head | body | tail with the body starting on a
+// 16-byte boundary and a multiple of 16 bytes long; the three pieces are reduced by the ordinary
+// kernels one after the other.  All of them fold into the caller's pre-filled output
+// (reduce-accessor semantics), so pieces along the reduction axis simply accumulate, and pieces of a
+// kept dim write disjoint outputs.  Arg-reductions keep their indices through the axis origin.
+// Returns 1 if the layout does not call for it.
+struct Peel {
+  int dim;                 // the contiguous dim
+  long long off[3], len[3];
+};
+
+bool plan_peel(const cnb_store_t* in, Peel& pl)
+{
+  static const bool enabled = [] {
+    const char* e = getenv("CNB_RED_PEEL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (!enabled || in->ndim < 1 || in->dtype >= CNB_NUM_DTYPES) return false;
+  const long long isz = (long long)dtype_size(in->dtype);
+  if (isz >= 16) return false;
+  long long total = 1;
+  int c = -1;
+  for (int d = 0; d < in->ndim; ++d) {
+    total *= in->shape[d];
+    if (in->shape[d] > 1 && in->strides[d] == isz) c = d;
+  }
+  if (c < 0 || total < (1LL << 20)) return false;
+  const long long n = in->shape[c], V = 16 / isz;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(in->ptr);
+  if (addr % isz != 0 || n < 64 * V) return false;
+  for (int d = 0; d < in->ndim; ++d)
+    if (d != c && in->shape[d] > 1 && in->strides[d] % 16 != 0) return false;
+  const long long head = (long long)((16 - addr % 16) % 16) / isz;
+  const long long body = ((n - head) / V) * V;
+  const long long tail = n - head - body;
+  if (head == 0 && tail == 0) return false;     // already aligned
+  pl.dim = c;
+  pl.off[0] = 0;           pl.len[0] = head;
+  pl.off[1] = head;        pl.len[1] = body;
+  pl.off[2] = head + body; pl.len[2] = tail;
+  return true;
+}
+
+int try_peel_axis(int op, int axis, const cnb_store_t* out, const cnb_store_t* in,
+                  long long axis_origin, cudaStream_t s)
+{
+  Peel pl;
+  if (axis < 0 || axis >= in->ndim || out->ndim != in->ndim || !plan_peel(in, pl)) return 1;
+  const long long isz = (long long)dtype_size(in->dtype);
+  for (int k = 0; k < 3; ++k) {
+    if (pl.len[k] == 0) continue;
+    cnb_store_t i2 = *in, o2 = *out;
+    i2.ptr = static_cast<char*>(in->ptr) + pl.off[k] * isz;
+    i2.shape[pl.dim] = pl.len[k];
+    o2.shape[pl.dim] = pl.len[k];
+    long long origin = axis_origin;
+    if (pl.dim == axis)
+      origin += pl.off[k];                                   // same outputs, later part of the axis
+    else
+      o2.ptr = static_cast<char*>(out->ptr) + pl.off[k] * out->strides[pl.dim];
+    // (a few very long rows: the aligned body is what the row split wants to see)
+    int rc = try_split_long_rows(op, axis, &o2, &i2, s);
+    if (rc == 1) rc = axis_red_dispatch(op, axis, &o2, &i2, nullptr, origin, s);
+    if (rc != CNB_OK) return rc;
+  }
+  return CNB_OK;
+}
+
+int scalar_red_dispatch(int op, const cnb_store_t* out, const cnb_store_t* in,
+                        const cnb_store_t* where, const int64_t* origin, const int64_t* gshape,
+                        const void* extra, cudaStream_t s)
+{
+  int rc;
+  if ((rc = scalar_red_group1(op, out, in, where, origin, gshape, extra, s)) != 1) return rc;
+  if ((rc = scalar_red_group2(op, out, in, where, origin, gshape, extra, s)) != 1) return rc;
+  if ((rc = scalar_red_group3(op, out, in, where, origin, gshape, extra, s)) != 1) return rc;
+  return set_error(CNB_ERR_BAD_ARG, "unknown reduction opcode %d", op);
+}
+
+// ---- full reduction of a pitched view -------------------------------------------------------------
+// SCALAR_UNARY_RED tiles the innermost dim; its 128-bit path serves FULL tiles only, so a pitched 2-D
+// view (every row ends in a partial tile, or starts off a 16-byte boundary) runs mostly on the
+// element-wise path (measured: x[1:-1, 1:-1].sum() of 16384^2 fp32 at 0.49 of the HBM peak; cutting
+// the view into head | body | tail for the same kernel made it worse, 0.26).  The axis kernels do not
+// have that problem: the view is reduced along its contiguous dim into one partial per row (ROW mode,
+// bulk-copy pipeline, with the misaligned ends peeled off), then the partials are reduced into the
+// caller's pre-filled output.  Value reductions whose partials can be reduced again, no mask.
+int try_rows_then_scalar(int op, const cnb_store_t* out, const cnb_store_t* in, cudaStream_t s)
+{
+  static const bool enabled = [] {
+    const char* e = getenv("CNB_RED_PEEL_SCALAR");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const int op2 = second_stage_op(op);
+  if (!enabled || op2 < 0 || in->ndim < 2 || in->dtype >= CNB_NUM_DTYPES || out->dtype >= CNB_NUM_DTYPES)
+    return 1;
+  const long long isz = (long long)dtype_size(in->dtype);
+  const long long vsz = (long long)dtype_size(out->dtype);
+  long long total = 1;
+  int c = -1;
+  for (int d = 0; d < in->ndim; ++d) {
+    total *= in->shape[d];
+    if (in->shape[d] > 1 && in->strides[d] < 0) return 1;
+    if (in->shape[d] > 1 && in->strides[d] == isz) c = d;
+  }
+  if (c < 0 || total < (1LL << 20)) return 1;
+  const long long n = in->shape[c], nrows = total / n;
+  if (n * isz < 4096 || nrows < 16) return 1;
+  // a dense view is one long row for SCALAR_UNARY_RED already
+  {
+    int order[CNB_MAX_DIM], k = 0;
+    for (int d = 0; d < in->ndim; ++d)
+      if (in->shape[d] > 1) order[k++] = d;
+    std::sort(order, order + k, [&](int a, int b) {
+      return std::llabs(in->strides[a]) < std::llabs(in->strides[b]);
+    });
+    long long expect = isz;
+    bool dense = true;
+    for (int i = 0; i < k && dense; ++i) {
+      dense = in->strides[order[i]] == expect;
+      expect *= in->shape[order[i]];
+    }
+    if (dense) return 1;
+  }
+  unsigned char ident[16];
+  if (!partial_identity(op2, out->dtype, ident)) return 1;
+  char* scratch = static_cast<char*>(pool_alloc((size_t)(nrows * vsz), s));
+  if (scratch == nullptr) return CNB_ERR_CUDA;
+  cnb_store_t flat{};
+  flat.ptr = scratch; flat.dtype = out->dtype; flat.ndim = 1;
+  flat.shape[0] = nrows; flat.strides[0] = vsz;
+  int rc = fill_value(&flat, ident, s);
+  if (rc == CNB_OK) {
+    // one partial per row: the output is promoted (stride 0) along the contiguous dim
+    cnb_store_t o2 = *in;
+    o2.ptr = scratch; o2.dtype = out->dtype;
+    long long acc = vsz;
+    for (int d = in->ndim - 1; d >= 0; --d) {
+      if (d == c) { o2.strides[d] = 0; continue; }
+      o2.strides[d] = acc;
+      acc *= in->shape[d];
+    }
+    rc = try_peel_axis(op, c, &o2, in, 0, s);
+    if (rc == 1) rc = axis_red_dispatch(op, c, &o2, in, nullptr, 0, s);
+  }
+  if (rc == CNB_OK) rc = scalar_red_dispatch(op2, out, &flat, nullptr, nullptr, nullptr, nullptr, s);
+  pool_free(scratch, s);
+  return rc;
+}
 }  // namespace
 }  // namespace cnb
 
@@ -335,11 +489,11 @@ int cnb_scalar_unary_red(int32_t op, const cnb_store_t* out, const cnb_store_t* 
   if (in->dtype >= CNB_NUM_DTYPES) return set_error(CNB_ERR_BAD_ARG, "reduction on a struct dtype");
   set_task_tag(CNB_OP_SCALAR_UNARY_RED, op, in->dtype);
   auto s = (cudaStream_t)stream;
-  int rc;
-  if ((rc = scalar_red_group1(op, out, in, where, origin, global_shape, extra, s)) != 1) return rc;
-  if ((rc = scalar_red_group2(op, out, in, where, origin, global_shape, extra, s)) != 1) return rc;
-  if ((rc = scalar_red_group3(op, out, in, where, origin, global_shape, extra, s)) != 1) return rc;
-  return set_error(CNB_ERR_BAD_ARG, "unknown reduction opcode %d", op);
+  if (where == nullptr) {
+    const int rc = try_rows_then_scalar(op, out, in, s);
+    if (rc != 1) return rc;
+  }
+  return scalar_red_dispatch(op, out, in, where, origin, global_shape, extra, s);
 }
 
 int cnb_unary_red(int32_t op, int32_t axis, const cnb_store_t* out, const cnb_store_t* in,
@@ -353,7 +507,9 @@ int cnb_unary_red(int32_t op, int32_t axis, const cnb_store_t* out, const cnb_st
   set_task_tag(CNB_OP_UNARY_RED, op, in->dtype);
   auto s = (cudaStream_t)stream;
   if (where == nullptr) {
-    const int rc = try_split_long_rows(op, axis, out, in, s);
+    int rc = try_peel_axis(op, axis, out, in, axis_origin, s);
+    if (rc != 1) return rc;
+    rc = try_split_long_rows(op, axis, out, in, s);
     if (rc != 1) return rc;
   }
   return axis_red_dispatch(op, axis, out, in, where, axis_origin, s);

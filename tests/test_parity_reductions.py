@@ -387,3 +387,71 @@ def test_multi_axis_reductions(shape, axes, dt):
                           np.count_nonzero(a, axis=axes))
     assert np.array_equal(A.sum(axis=axes, keepdims=True).__array__().shape,
                           a.sum(axis=axes, keepdims=True).shape)
+
+
+PEEL_VIEWS = [
+    ((1030, 1104), np.s_[1:-1, 1:-1]),        # head + body + tail
+    ((1030, 1104), np.s_[:, 3:]),             # head only
+    ((1030, 1104), np.s_[2:, :-5]),           # tail only
+    ((4, 515, 1104), np.s_[:, 1:-1, 1:-7]),   # 3-D, two kept dims
+]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32, np.uint8, np.float16, np.int64],
+                         ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("case", range(len(PEEL_VIEWS)))
+def test_reductions_of_misaligned_pitched_views(case, dt):
+    """Views whose rows keep a 16-byte pitch but start / end inside a 16-byte word (x[1:-1, 1:-1]) are
+    reduced as head | body | tail (capi.cu try_peel_axis / try_peel_scalar): every axis and the full
+    reduction against the oracle on a contiguous copy of the view, arg-reductions with their global
+    indices, ties across the pieces resolved to the first occurrence."""
+    import cunumeric_b200 as cn
+
+    dt = np.dtype(dt)
+    shape, sl = PEEL_VIEWS[case]
+    rng = pu.rng_for("peel", dt.name, case)
+    for op in ("SUM", "MAX", "MIN", "ARGMAX", "ARGMIN", "COUNT_NONZERO", "ANY"):
+        base = red_input(op, dt, shape, rng)
+        view = np.ascontiguousarray(base[sl])
+        assert view.size >= 1 << 20
+        V = cn.array(base)[sl]
+        n_eps = view.size
+        for axis in list(range(view.ndim)) + [None]:
+            if axis is None and op == "SUM" and dt == np.float16:
+                continue   # 10^6 terms accumulated in fp16 by the oracle: not a usable expectation
+            if axis is None:
+                exp = ref.scalar_unary_red(op, view, initial=python_prefill(op, dt))
+            else:
+                exp = ref.unary_red(op, view, axis, initial=python_prefill(op, dt))
+            if op in ref.ARG_RED:
+                got = (V.argmax(axis=axis) if op == "ARGMAX" else V.argmin(axis=axis)).__array__()
+            elif op == "COUNT_NONZERO":
+                got = cn.count_nonzero(V, axis=axis).__array__()
+                exp = np.count_nonzero(view, axis=axis)
+                assert np.array_equal(got, exp), (op, axis)
+                continue
+            elif op == "ANY":
+                got = V.any(axis=axis).__array__()
+            else:
+                got = getattr(V, op.lower())(axis=axis).__array__()
+            check_reduction(op, view, np.asarray(got), exp, n_eps if axis is None else view.shape[axis],
+                            f"peel {op}/{dt.name} case {case} axis {axis}")
+    # ties: the same extreme in the head, the body and the tail of a row -> first occurrence wins
+    t = np.zeros(shape, dtype=dt)
+    tv = t[sl]
+    tv[..., 0] = 3
+    tv[..., tv.shape[-1] // 2] = 3
+    tv[..., -1] = 3
+    T = cn.array(t)[sl]
+    assert np.array_equal(T.argmax(axis=tv.ndim - 1).__array__(), np.zeros(tv.shape[:-1], np.int64))
+    assert int(T.argmax()) == 0
+    tv[..., 0] = 0
+    T = cn.array(t)[sl]
+    assert np.array_equal(T.argmax(axis=tv.ndim - 1).__array__(),
+                          np.full(tv.shape[:-1], tv.shape[-1] // 2, np.int64))
+    assert int(T.argmax()) == tv.shape[-1] // 2
+    # a pre-filled output is folded in once, not once per piece
+    if dt.kind == "f":
+        ones = cn.array(np.ones(shape, dtype=dt))[sl]
+        got = ones.sum(axis=ones.ndim - 1, initial=5).__array__()
+        assert np.array_equal(got, np.full(tv.shape[:-1], tv.shape[-1] + 5, dtype=dt)) or dt == np.float16

@@ -17,7 +17,8 @@ BINARY = {
     int(BinaryOpCode.ADD): np.add, int(BinaryOpCode.SUBTRACT): np.subtract,
     int(BinaryOpCode.MULTIPLY): np.multiply, int(BinaryOpCode.MAXIMUM): np.maximum,
     int(BinaryOpCode.MINIMUM): np.minimum, int(BinaryOpCode.GREATER): np.greater,
-    int(BinaryOpCode.LESS): np.less,
+    int(BinaryOpCode.LESS): np.less, int(BinaryOpCode.LOGICAL_AND): np.logical_and,
+    int(BinaryOpCode.LOGICAL_OR): np.logical_or,
 }
 UNARY = {
     int(UnaryOpCode.COPY): lambda x: x.copy(), int(UnaryOpCode.NEGATIVE): np.negative,

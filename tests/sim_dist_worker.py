@@ -59,6 +59,32 @@ class SimCommLib(sim_backend.SimLib):
         return 0
 
 
+    # ---- collectives on dense buffers: gather the raw bytes over gloo, fold locally in rank order
+    def _gather(self, src, nbytes):
+        mine = np.frombuffer((ctypes.c_uint8 * nbytes).from_address(src), dtype=np.uint8).copy()
+        outs = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(dist.get_world_size())]
+        dist.all_gather(outs, torch.from_numpy(mine))
+        return [t.numpy() for t in outs]
+
+    def cnb_comm_allgather(self, comm, src, dst, nbytes, stream):
+        for r, raw in enumerate(self._gather(src, nbytes)):
+            ctypes.memmove(dst + r * nbytes, raw.ctypes.data, nbytes)
+        return 0
+
+    def cnb_comm_allreduce(self, comm, src, dst, count, dtype, red, stream):
+        from cunumeric_b200.config import UnaryRedCode
+
+        dt = np.dtype(sim_backend.DTYPES[dtype])
+        parts = np.stack([raw.view(dt) for raw in self._gather(src, count * dt.itemsize)])
+        fold = {int(UnaryRedCode.SUM): lambda p: p.sum(axis=0, dtype=dt),
+                int(UnaryRedCode.PROD): lambda p: p.prod(axis=0, dtype=dt),
+                int(UnaryRedCode.MAX): lambda p: p.max(axis=0), int(UnaryRedCode.MIN): lambda p: p.min(axis=0),
+                int(UnaryRedCode.ALL): lambda p: p.all(axis=0), int(UnaryRedCode.ANY): lambda p: p.any(axis=0)}
+        res = np.ascontiguousarray(fold[red](parts).astype(dt))
+        ctypes.memmove(dst, res.ctypes.data, res.nbytes)
+        return 0
+
+
 def main() -> None:
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -100,6 +126,27 @@ def main() -> None:
         A[1:-1] = up * 0.25
         a0[1:-1] = (a0[1:-1] + a0[0:-2] + a0[2:]) * 0.25
     assert np.array_equal(A.__array__(), a0), f"rank {rank}: shifted-row update mismatch"
+    # ---- reductions of partitioned arrays: local partial, then the combine across the ranks
+    # (ncclAllReduce, or ncclAllGather + the library's own fold for floating MAX / MIN), then the fold
+    # into the pre-filled result
+    x = rng.integers(-9, 10, size=(37, 6)).astype(np.int64)
+    X = cn.array(x)
+    assert isinstance(X._thunk, PartitionedArray)
+    assert int(X.sum()) == int(x.sum()) and int(X.max()) == int(x.max()) and int(X.min()) == int(x.min())
+    assert int(X.sum(initial=100)) == int(x.sum()) + 100
+    assert np.array_equal(X.sum(axis=0).__array__(), x.sum(axis=0))           # partitioned axis: combine
+    assert np.array_equal(X.max(axis=0).__array__(), x.max(axis=0))
+    assert np.array_equal(X.sum(axis=1).__array__(), x.sum(axis=1))           # local
+    assert np.array_equal(X.min(axis=1).__array__(), x.min(axis=1))
+    assert np.array_equal(X.sum(axis=0, keepdims=True).__array__(), x.sum(axis=0, keepdims=True))
+    assert bool((X > -100).all()) and not bool((X > 100).any())
+    assert int(cn.count_nonzero(X)) == int(np.count_nonzero(x))
+    f = rng.normal(size=(29, 5))
+    F = cn.array(f)
+    assert float(F.max()) == f.max() and float(F.min()) == f.min()             # gather + fold path
+    assert np.array_equal(F.max(axis=0).__array__(), f.max(axis=0))
+    assert np.allclose(float(F.sum()), f.sum(), rtol=1e-13)
+    assert np.allclose(F.sum(axis=0).__array__(), f.sum(axis=0), rtol=1e-13)
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")

@@ -306,3 +306,83 @@ def test_multi_axis_reductions_run_axis_by_axis(sim):
         A.sum(axis=(1, 1))
     # all axes named explicitly: the scalar reduction, as before
     assert int(A.sum(axis=(0, 1, 2, 3))) == int(a.sum())
+
+
+def test_tma_launch_runs_a_queued_exchange_between_boundary_and_interior_tiles(sim, monkeypatch):
+    """Host side of fusion._launch_tma with an Overlap (opt-in, CUNUMERIC_B200_HALO_OVERLAP=1): the
+    sequence of calls on the two streams, and the tile rows each launch covers.  The device side (the
+    generated kernel's ty_split / ty_skip mapping) is covered by tests/dist_worker.py on GPUs."""
+    import ctypes
+
+    from cunumeric_b200 import fusion
+    from cunumeric_b200.config import BinaryOpCode
+    from cunumeric_b200.runtime import runtime
+    from cunumeric_b200.store import Store
+
+    tr, tc = fusion.TMA_TR, fusion.TMA_TC
+    rows, cols, item = 24 * tr + 2, 4 * tc + 2, 8
+    pitch = cols * item
+    grid = Store.empty((rows, cols), np.float64)
+    centre = grid.slice(0, slice(1, rows - 1)).slice(1, slice(1, cols - 1))
+    north = grid.slice(0, slice(0, rows - 2)).slice(1, slice(1, cols - 1))
+    out_w, in_w = [fusion._Window(centre)], [fusion._Window(centre), fusion._Window(north)]
+    shape = centre.shape
+    sig = (((11, False), (11, False)), (("B", int(BinaryOpCode.ADD), 0, (0, 1), 2, 11),), ((2, 11),))
+    dims = fusion._canonical(shape, [w.strides for w in out_w + in_w])
+    lay, groups = fusion._tma_layout(sig, shape, out_w, in_w, dims)
+    geo = fusion._tma_geometry(sig, lay)
+    tail_cls = fusion._tma_params_type(len(geo["groups"]), 1, 0)
+    monkeypatch.setattr(fusion, "_lookup_tma", lambda s, l: (1, geo, tail_cls, None))
+
+    log = []
+
+    def launch(kern, ops, ng, tail_ref, tail_bytes, smem, num_tiles, elements, algo, ntasks, cps, stream):
+        t = ctypes.cast(tail_ref, ctypes.POINTER(tail_cls)).contents
+        assert t.num_tiles == num_tiles
+        log.append(("launch", stream, t.num_tiles // t.tiles_x, t.ty_split, t.ty_skip))
+        return 0
+
+    lib = sim
+    lib.cnb_launch_fused_tma = launch
+    lib.cnb_stream_create = lambda: 777
+    lib.cnb_event_create = lambda: 55
+    lib.cnb_event_record = lambda ev, stream: log.append(("record", stream)) or 0
+    lib.cnb_stream_wait_event = lambda stream, ev: log.append(("wait", stream)) or 0
+    monkeypatch.setattr(runtime, "_comm_stream", None)
+    monkeypatch.setattr(runtime, "_event_pool", [])
+
+    renamed = {id(grid.buffer): (out_w[0], out_w[0].offset, rows - 2, (cols - 2) * item, pitch)}
+    ptrs = [grid.buffer.ptr + w.offset for w in out_w + in_w]
+    tiles_y = -(-(rows - 2) // tr)
+    inner, n_rows = dims[1][0], dims[0][0]
+    row_st = dims[0][1]
+    committed = []
+
+    def run(overlap):
+        del log[:], committed[:]
+        ok = fusion._launch_tma(sig, lay, groups, inner, n_rows, row_st, out_w, in_w, ptrs, 0, 1,
+                                lambda: committed.append(len(log)), renamed, overlap)
+        assert ok and committed, "the launch must commit the renamed blocks itself"
+        return list(log)
+
+    # no exchange queued behind the chain: one launch over every tile row
+    assert run(None) == [("launch", runtime.stream, tiles_y, tiles_y, 0)]
+    # an exchange of the first / last owned row: boundary tile rows, exchange on the communication
+    # stream behind an event, interior next to it, compute stream waits for the exchange at the end
+    send = [(1 * pitch, 2 * pitch), ((rows - 2) * pitch, (rows - 1) * pitch)]
+    recv = [(0, pitch), ((rows - 1) * pitch, rows * pitch)]
+    ov = fusion.Overlap(grid.buffer, send, recv, lambda stream: log.append(("exchange", stream)))
+    seq = run(ov)
+    assert seq == [("launch", runtime.stream, 2, 1, tiles_y - 2),      # tile rows 0 and tiles_y - 1
+                   ("record", runtime.stream), ("wait", 777), ("exchange", 777), ("record", 777),
+                   ("launch", runtime.stream, tiles_y - 2, 0, 1),      # tile rows 1 .. tiles_y - 2
+                   ("wait", runtime.stream)]
+    assert ov.done and committed == [1], "blocks are adopted right after the boundary launch"
+    # first rank: nothing to exchange above -> only the last tile row is boundary
+    ov = fusion.Overlap(grid.buffer, send[1:], recv[1:], lambda stream: log.append(("exchange", stream)))
+    seq = run(ov)
+    assert seq[0] == ("launch", runtime.stream, 1, 0, tiles_y - 1)
+    assert seq[5] == ("launch", runtime.stream, tiles_y - 1, 0, 0)
+    # an exchange that is already done (or a chain that cannot run around it) changes nothing
+    ov.done = True
+    assert run(ov) == [("launch", runtime.stream, tiles_y, tiles_y, 0)]

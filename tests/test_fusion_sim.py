@@ -386,3 +386,81 @@ def test_tma_launch_runs_a_queued_exchange_between_boundary_and_interior_tiles(s
     # an exchange that is already done (or a chain that cannot run around it) changes nothing
     ov.done = True
     assert run(ov) == [("launch", runtime.stream, tiles_y, tiles_y, 0)]
+
+
+def run_reduction_program(seed: int, xp, steps: int = 50):
+    """Random int64 programs (wrap-around arithmetic is exact, so any association order gives the
+    same bits) that mix elementwise tasks on views, in-place updates and reductions — full ones
+    (which may join the open chain as its last task) and axis ones — whose results feed later tasks."""
+    rng = np.random.default_rng(seed)
+    data = np.random.default_rng(2000 + seed)
+    base = {k: xp.array(data.integers(-9, 10, size=(R, C)).astype(np.int64)) for k in "abc"}
+    temps, scalars, checks = {}, [], []
+    ops = ["add", "subtract", "multiply", "maximum", "minimum"]
+
+    def pick(shape_kind):
+        names = [k for k, v in temps.items() if v[0] == shape_kind]
+        if names and rng.random() < 0.6:
+            return temps[names[rng.integers(len(names))]][1]
+        b = base["abc"[rng.integers(3)]]
+        views = SUB if shape_kind == "sub" else FULL
+        return b[views[rng.integers(len(views))]]
+
+    for step in range(steps):
+        kind = rng.integers(10)
+        shape_kind = "sub" if rng.random() < 0.6 else "full"
+        op = getattr(xp, ops[rng.integers(len(ops))])
+        if kind <= 2:
+            x = pick(shape_kind)
+            r = rng.random()
+            if r < 0.5:
+                y = pick(shape_kind)
+            elif r < 0.75 or not scalars:
+                y = int(rng.integers(1, 5))
+            else:
+                y = scalars[rng.integers(len(scalars))]        # a reduction result as 0-d operand
+            temps[f"t{step}"] = (shape_kind, op(x, y))
+        elif kind == 3:
+            dst = base["abc"[rng.integers(3)]]
+            views = SUB if shape_kind == "sub" else FULL
+            dst[views[rng.integers(len(views))]] = pick(shape_kind)
+        elif kind == 4:
+            dst = base["abc"[rng.integers(3)]]
+            views = SUB if shape_kind == "sub" else FULL
+            v = dst[views[rng.integers(len(views))]]
+            v += pick(shape_kind)
+        elif kind == 5:       # full reduction, often of a value the open chain has just produced
+            x = pick(shape_kind)
+            if rng.random() < 0.6:
+                x = op(x, pick(shape_kind))
+            red = ["sum", "max", "min"][rng.integers(3)]
+            scalars.append(getattr(x, red)())
+        elif kind == 6:       # axis reduction, broadcast back along the reduced axis
+            x = pick(shape_kind)
+            axis = int(rng.integers(2))
+            red = ["sum", "max", "min"][rng.integers(3)]
+            r_ = getattr(x, red)(axis=axis, keepdims=True)
+            temps[f"t{step}"] = (shape_kind, xp.add(x, r_))
+        elif kind == 7 and temps:
+            temps.pop(list(temps)[rng.integers(len(temps))])
+        elif kind == 8 and temps:
+            name = list(temps)[rng.integers(len(temps))]
+            checks.append(np.array(temps[name][1]))
+        elif kind == 9 and scalars:
+            checks.append(np.array(scalars[rng.integers(len(scalars))]))
+    final = [np.array(v) for v in base.values()] + [np.array(v[1]) for v in temps.values()] + \
+            [np.array(s) for s in scalars]
+    return checks + final
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_programs_with_reductions_match_numpy(sim, seed):
+    import cunumeric_b200 as cn
+
+    with np.errstate(over="ignore"):
+        got = run_reduction_program(seed, cn)
+        exp = run_reduction_program(seed, np)
+    assert len(got) == len(exp)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        assert g.shape == e.shape and g.dtype == e.dtype, (seed, i, g.shape, e.shape, g.dtype, e.dtype)
+        assert np.array_equal(g, e), (seed, i, np.argwhere(g != e)[:3])

@@ -85,6 +85,63 @@ class SimCommLib(sim_backend.SimLib):
         return 0
 
 
+PR, PC = 23, 9
+# (view, first base row): the row offset decides which neighbours' rows a task needs
+P_SUB = [(np.s_[1:-1, 1:-1], 1), (np.s_[0:-2, 1:-1], 0), (np.s_[2:, 1:-1], 2), (np.s_[1:-1, 0:-2], 1),
+         (np.s_[1:-1, 2:], 1)]
+
+
+def partitioned_program(seed: int, xp, steps: int = 40):
+    """Outputs are always tiled like the interior rows (offset 1), so every operand is at most one
+    row away from its owner — the halo depth (a farther operand raises NotImplementedError)."""
+    rng = np.random.default_rng(seed)
+    data = np.random.default_rng(3000 + seed)
+    base = {k: xp.array(data.integers(-9, 10, size=(PR, PC)).astype(np.int64)) for k in "ab"}
+    temps, scalars, checks = [], [], []
+    ops = ["add", "subtract", "multiply", "maximum", "minimum"]
+
+    def view(only_centre_rows=False):
+        cands = [v for v, r0 in P_SUB if r0 == 1 or not only_centre_rows]
+        return base["ab"[rng.integers(2)]][cands[rng.integers(len(cands))]]
+
+    def operand(first=False):
+        if temps and rng.random() < 0.5:
+            return temps[rng.integers(len(temps))]
+        return view(only_centre_rows=first)
+
+    for step in range(steps):
+        kind = rng.integers(9)
+        op = getattr(xp, ops[rng.integers(len(ops))])
+        if kind <= 2:
+            x = operand(first=True)
+            r = rng.random()
+            y = operand() if r < 0.6 else (int(rng.integers(1, 5)) if r < 0.8 or not scalars
+                                           else scalars[rng.integers(len(scalars))])
+            temps.append(op(x, y))
+        elif kind == 3:      # assignment into a view (any row offset) from an interior-tiled operand
+            v, r0 = P_SUB[rng.integers(len(P_SUB))]
+            base["ab"[rng.integers(2)]][v] = operand(first=True)
+        elif kind == 4:      # in-place update of an interior-tiled view
+            dst = view(only_centre_rows=True)
+            dst += operand()
+        elif kind == 5:      # full reduction (local partial + combine across the ranks)
+            x = operand(first=True)
+            if rng.random() < 0.5:
+                x = op(x, operand())
+            scalars.append(getattr(x, ["sum", "max", "min"][rng.integers(3)])())
+        elif kind == 6:      # axis reduction broadcast back: axis 1 is local, axis 0 needs the combine
+            x = operand(first=True)
+            axis = int(rng.integers(2))
+            r_ = getattr(x, ["sum", "max", "min"][rng.integers(3)])(axis=axis, keepdims=True)
+            temps.append(xp.add(x, r_))
+        elif kind == 7 and temps:
+            temps.pop(rng.integers(len(temps)))
+        elif kind == 8 and temps:
+            checks.append(np.array(temps[rng.integers(len(temps))]))
+    return checks + [np.array(v) for v in base.values()] + [np.array(t) for t in temps] + \
+        [np.array(s_) for s_ in scalars]
+
+
 def main() -> None:
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -147,6 +204,17 @@ def main() -> None:
     assert np.array_equal(F.max(axis=0).__array__(), f.max(axis=0))
     assert np.allclose(float(F.sum()), f.sum(), rtol=1e-13)
     assert np.allclose(F.sum(axis=0).__array__(), f.sum(axis=0), rtol=1e-13)
+    # ---- random programs on partitioned arrays (the same text on every rank and for NumPy): shifted
+    # views, temporaries, assignments into views, in-place updates, reductions fed back as operands.
+    # int64 wrap-around arithmetic is exact, so every association order gives the same bits.
+    for seed in range(int(os.environ.get("SIM_PROGRAMS", "6"))):
+        with np.errstate(over="ignore"):
+            got = partitioned_program(seed, cn)
+            exp = partitioned_program(seed, np)
+        assert len(got) == len(exp)
+        for i, (g, e) in enumerate(zip(got, exp)):
+            assert g.shape == e.shape and np.array_equal(g, e), \
+                f"rank {rank}: program {seed} value {i} differs (mode {mode}): {np.argwhere(g != e)[:3].tolist()}"
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")

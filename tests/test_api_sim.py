@@ -98,3 +98,91 @@ def test_unary_result_dtypes_match_numpy(sim, op):  # noqa: F811
     assert cn.negative(a, dtype=np.float64).dtype == np.float64
     out = cn.empty((4,), dtype=np.int64)
     assert cn.negative(a, out=out) is out and np.array_equal(np.array(out), -np.arange(4))
+
+
+def _random_key(rng, shape):
+    key = []
+    nd = len(shape)
+    n_idx = int(rng.integers(0, nd + 1))
+    for d in range(n_idx):
+        n = shape[d]
+        r = rng.random()
+        if r < 0.25 and n > 0:
+            key.append(int(rng.integers(-n, n)))
+        elif r < 0.9:
+            start = None if rng.random() < 0.3 else int(rng.integers(-n - 1, n + 2))
+            stop = None if rng.random() < 0.3 else int(rng.integers(-n - 1, n + 2))
+            step = None if rng.random() < 0.5 else int(rng.choice([-3, -2, -1, 1, 2, 3]))
+            key.append(slice(start, stop, step))
+        else:
+            key.append(slice(None))
+    if rng.random() < 0.2 and n_idx < nd:
+        key.insert(int(rng.integers(0, len(key) + 1)), Ellipsis)
+    return tuple(key)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_basic_indexing_matches_numpy(sim, seed):  # noqa: F811
+    """Store view algebra behind ndarray.__getitem__ / __setitem__ (deferred.py:_basic_index; the
+    reference's get_item / set_item, deferred.py:927-1094): random integer / slice / Ellipsis keys incl.
+    negative steps, out-of-range bounds and empty results; views of views; assignment of arrays and
+    scalars through a view."""
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(150):
+        shape = tuple(int(rng.integers(1, 6)) for _ in range(int(rng.integers(1, 5))))
+        a = rng.integers(-50, 50, size=shape).astype(np.int64)
+        A = cn.array(a)
+        key = _random_key(rng, shape)
+        try:
+            exp = a[key]
+        except IndexError:      # an integer that lands on a shorter axis behind an Ellipsis
+            with pytest.raises(IndexError):
+                A[key]
+            continue
+        got = A[key]
+        g = np.array(got)
+        assert g.shape == exp.shape and np.array_equal(g, exp), (shape, key)
+        key2 = _random_key(rng, exp.shape) if exp.ndim else ()
+        try:
+            exp2 = exp[key2]
+        except IndexError:
+            exp2 = None
+        if exp2 is not None:
+            assert np.array_equal(np.array(got[key2]), exp2), (shape, key, key2)
+        val = rng.integers(-9, 9, size=exp.shape).astype(np.int64)
+        a2, A2 = a.copy(), cn.array(a)
+        a2[key] = val
+        A2[key] = cn.array(val) if val.ndim else int(val)
+        assert np.array_equal(np.array(A2), a2), (shape, key)
+        a2[key] = 7
+        A2[key] = 7
+        assert np.array_equal(np.array(A2), a2), (shape, key)
+    with pytest.raises(IndexError):
+        cn.array(np.arange(5))[7]
+    with pytest.raises(IndexError):
+        cn.array(np.ones((2, 3)))[0, 1, 2]
+
+
+def test_shape_manipulation_matches_numpy(sim):  # noqa: F811
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(9)
+    for _ in range(60):
+        shape = tuple(int(rng.integers(1, 5)) for _ in range(int(rng.integers(1, 5))))
+        a = rng.integers(-50, 50, size=shape).astype(np.int64)
+        A = cn.array(a)
+        perm = tuple(int(p) for p in rng.permutation(len(shape)))
+        assert np.array_equal(np.array(A.transpose(perm)), a.transpose(perm))
+        assert np.array_equal(np.array(A.T), a.T)
+        i, j = int(rng.integers(len(shape))), int(rng.integers(len(shape)))
+        assert np.array_equal(np.array(A.swapaxes(i, j)), a.swapaxes(i, j))
+        assert np.array_equal(np.array(A.ravel()), a.ravel())
+        assert np.array_equal(np.array(A.T.flatten()), a.T.flatten())
+        assert np.array_equal(np.array(A.reshape(-1)), a.reshape(-1))
+        assert np.array_equal(np.array(A.T.reshape(a.size)), a.T.reshape(a.size))   # needs a copy
+        assert np.array_equal(np.array(cn.squeeze(A)), np.squeeze(a))
+        assert A.T.shape == a.T.shape and A.size == a.size and A.ndim == a.ndim
+    with pytest.raises(ValueError):
+        cn.array(np.arange(6)).reshape(4, 2)

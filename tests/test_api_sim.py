@@ -186,3 +186,40 @@ def test_shape_manipulation_matches_numpy(sim):  # noqa: F811
         assert A.T.shape == a.T.shape and A.size == a.size and A.ndim == a.ndim
     with pytest.raises(ValueError):
         cn.array(np.arange(6)).reshape(4, 2)
+
+
+def test_reduction_api_matches_numpy(sim):  # noqa: F811
+    """ndarray.sum / prod / max / min / all / any (array.py:_perform_unary_reduction; reference
+    array.py:4323-4418): axis (negative too) / keepdims / initial / out= on arrays and on stepped or
+    reversed views; int64 data, so every association order gives the same bits."""
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(3)
+    for _ in range(250):
+        nd = int(rng.integers(1, 5))
+        shape = tuple(int(rng.integers(1, 5)) for _ in range(nd))
+        a = rng.integers(-5, 6, size=shape).astype(np.int64)
+        A = cn.array(a)
+        if rng.random() < 0.4:
+            key = tuple(slice(None, None, int(rng.choice([1, -1, 2]))) for _ in range(nd))
+            a, A = a[key], A[key]
+        axis = None if rng.random() < 0.25 else int(rng.integers(-nd, nd))
+        keep = bool(rng.random() < 0.5)
+        name = ["sum", "prod", "max", "min", "all", "any"][rng.integers(6)]
+        kw = {}
+        if name in ("sum", "prod", "max", "min") and rng.random() < 0.3:
+            kw["initial"] = int(rng.integers(-3, 4))
+        exp = getattr(a, name)(axis=axis, keepdims=keep, **kw)
+        g = np.array(getattr(A, name)(axis=axis, keepdims=keep, **kw))
+        assert g.shape == np.shape(exp) and g.dtype == np.asarray(exp).dtype, (shape, name, axis, keep)
+        assert np.array_equal(g, exp), (shape, name, axis, keep, kw)
+        if name in ("sum", "max") and rng.random() < 0.3:
+            out = cn.empty(np.shape(exp), dtype=np.int64)
+            assert getattr(A, name)(axis=axis, keepdims=keep, out=out, **kw) is out
+            assert np.array_equal(np.array(out), exp)
+    A = cn.array(np.ones((3, 4), dtype=np.int64))
+    with pytest.raises(ValueError):
+        A.sum(axis=0, out=cn.empty((3,), dtype=np.int64))
+    with pytest.raises((ValueError, np.exceptions.AxisError)):
+        A.sum(axis=2)
+    assert cn.array(np.array([True, False, True])).sum().dtype == np.int32   # array.py:3146 (bool -> int32)

@@ -223,3 +223,35 @@ def test_reduction_api_matches_numpy(sim):  # noqa: F811
     with pytest.raises((ValueError, np.exceptions.AxisError)):
         A.sum(axis=2)
     assert cn.array(np.array([True, False, True])).sum().dtype == np.int32   # array.py:3146 (bool -> int32)
+
+
+def test_where_and_astype_dtypes_match_numpy(sim):  # noqa: F811
+    """module.where (reference module.py:3493-3541, array.py:4455-4470: common type of the two
+    branches, mask broadcast) and ndarray.astype for every dtype pair."""
+    import warnings
+
+    import cunumeric_b200 as cn
+
+    rng = np.random.default_rng(0)
+    for da in DTYPES:
+        a = np.arange(6).reshape(2, 3).astype(da)
+        for db in DTYPES:
+            b = (np.arange(3) + 10).astype(db)
+            m = rng.random((2, 3)) < 0.5
+            exp = np.where(m, a, b)
+            g = np.array(cn.where(cn.array(m), cn.array(a), cn.array(b)))
+            assert g.dtype == exp.dtype and np.array_equal(g, exp), (np.dtype(da).name, np.dtype(db).name)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")      # complex -> real discards the imaginary part
+                exp = a.astype(db)
+                g = np.array(cn.array(a).astype(db))
+            assert g.dtype == exp.dtype and np.array_equal(g, exp), (np.dtype(da).name, np.dtype(db).name)
+        for sc in (2, 2.5, True, 1j):
+            m = rng.random((2, 3)) < 0.5
+            exp = np.where(m, a, sc)
+            g = np.array(cn.where(cn.array(m), cn.array(a), sc))
+            assert g.dtype == exp.dtype and np.array_equal(g, exp), (np.dtype(da).name, sc)
+    x = cn.array(np.arange(4.0))
+    with pytest.raises(TypeError):
+        x.astype(np.int32, casting="safe")
+    assert x.astype(np.float64, copy=False) is x

@@ -299,9 +299,11 @@ class PartitionedArray:
         fusion.enqueue(lambda: self._run_transfers(plan, lo - m.lead, m.local), overlap)
         m.ghost_valid = True
 
-    def _ensure_aligned_with(self, out_part: RowPartition) -> None:
+    def _ensure_aligned_with(self, out_part: RowPartition) -> int:
         """This view is about to be read row for row by a task whose output rows are tiled by
-        `out_part`: make the rows every rank needs available (collective).  The classification is a
+        `out_part`: make the rows every rank needs available (collective) and return where they are
+        — 0: owned, 1: owned + ghost rows (refreshed here), 2: farther away (the caller fetches them,
+        `_fetch_rows`).  The classification is a
         pure function of the two tilings and is cached (temporaries of a loop body are new arrays with
         the same tiling every iteration)."""
         m = self.meta
@@ -325,31 +327,32 @@ class PartitionedArray:
             _ALIGN[key] = kind
         if kind == 1:
             self.exchange_halo()
-        elif kind == 2:
-            raise NotImplementedError(
-                "operand rows are farther than the halo depth from their owner: general "
-                "redistribution is not implemented (use gather() / a larger halo)")
+        return kind
 
-    def _ensure_rows(self, needs: Sequence[Tuple[int, int]]) -> None:
-        """`needs[r]` = BASE rows rank r is about to read.  Collective."""
+    def _fetch_rows(self, out_part: RowPartition) -> DeferredArray:
+        """Rows of this view that are farther than the halo depth from their owners, for a task whose
+        output rows are tiled by `out_part`: every rank receives the rows it is about to read into a
+        temporary block (one grouped send/recv, `plan_fetch`; rows it owns itself are copied locally)
+        — the general redistribution Legion performs when an operand's tiling is not aligned with the
+        output's.  Collective."""
         m = self.meta
-        within_owned = within_halo = True
-        for r, (nlo, nhi) in enumerate(needs):
-            if nhi <= nlo:
-                continue
-            lo, hi = m.part.bounds(r)
-            if nlo < lo or nhi > hi:
-                within_owned = False
-            if nlo < lo - m.halo or nhi > hi + m.halo:
-                within_halo = False
-        if within_owned:
-            return
-        if within_halo:
-            self.exchange_halo()
-            return
-        raise NotImplementedError(
-            "operand rows are farther than the halo depth from their owner: general "
-            "redistribution is not implemented (use gather() / a larger halo)")
+        rank = runtime.rank
+        needs = []
+        for r in range(out_part.world):
+            a, b = out_part.bounds(r)
+            needs.append((self.row0 + a, self.row0 + b) if b > a else (0, 0))
+        nlo, nhi = needs[rank]
+        tmp = DeferredArray(Store.empty((max(0, nhi - nlo),) + m.gshape[1:], m.dtype))
+        lo, hi = m.part.bounds(rank)
+        a, b = max(nlo, lo), min(nhi, hi)
+        if b > a:
+            DeferredArray(tmp.base.slice(0, slice(a - nlo, b - nlo))).copy(
+                PartitionedArray(m).local_rows(a, b), deep=True)
+        self._run_transfers(plan_fetch(m.part, needs), nlo, tmp)
+        base = tmp.base
+        if self.inner_key:
+            base = _basic_index(base, (slice(None),) + self.inner_key)
+        return DeferredArray(base)
 
     def gather(self) -> DeferredArray:
         """Replicated copy of the whole view on every rank (collective)."""
@@ -376,8 +379,11 @@ class PartitionedArray:
         if type(src) is PartitionedArray:
             sshape, myshape = src.shape, self.shape
             if len(sshape) == len(myshape) and sshape[0] == myshape[0]:
-                src._ensure_aligned_with(self.part)
-                return src.local_rows(vlo, vhi)
+                if src._ensure_aligned_with(self.part) == 2:
+                    return src._fetch_rows(self.part)
+                # (a rank that owns none of the output rows takes part in the collectives above and
+                # then has nothing to read)
+                return src.local_rows(vlo, vhi) if vhi > vlo else None
             # cannot be aligned row-for-row with the output (lower rank, or broadcast along the
             # partitioned axis): replicate it (collective) and fall through to the replicated rules
             src = src.gather()

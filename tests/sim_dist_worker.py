@@ -91,9 +91,11 @@ P_SUB = [(np.s_[1:-1, 1:-1], 1), (np.s_[0:-2, 1:-1], 0), (np.s_[2:, 1:-1], 2), (
          (np.s_[1:-1, 2:], 1)]
 
 
-def partitioned_program(seed: int, xp, steps: int = 40):
-    """Outputs are always tiled like the interior rows (offset 1), so every operand is at most one
-    row away from its owner — the halo depth (a farther operand raises NotImplementedError)."""
+def partitioned_program(seed: int, xp, steps: int = 40, free: bool = False):
+    """free=False: outputs are always tiled like the interior rows (offset 1), so every operand is at
+    most one row away from its owner — the halo depth, served by the ghost rows.  free=True: any view
+    may come first, so operands can be two rows away from their owners and are fetched into temporary
+    blocks (PartitionedArray._fetch_rows)."""
     rng = np.random.default_rng(seed)
     data = np.random.default_rng(3000 + seed)
     base = {k: xp.array(data.integers(-9, 10, size=(PR, PC)).astype(np.int64)) for k in "ab"}
@@ -101,7 +103,7 @@ def partitioned_program(seed: int, xp, steps: int = 40):
     ops = ["add", "subtract", "multiply", "maximum", "minimum"]
 
     def view(only_centre_rows=False):
-        cands = [v for v, r0 in P_SUB if r0 == 1 or not only_centre_rows]
+        cands = [v for v, r0 in P_SUB if r0 == 1 or not only_centre_rows or free]
         return base["ab"[rng.integers(2)]][cands[rng.integers(len(cands))]]
 
     def operand(first=False):
@@ -204,17 +206,34 @@ def main() -> None:
     assert np.array_equal(F.max(axis=0).__array__(), f.max(axis=0))
     assert np.allclose(float(F.sum()), f.sum(), rtol=1e-13)
     assert np.allclose(F.sum(axis=0).__array__(), f.sum(axis=0), rtol=1e-13)
+    # ---- operands whose rows are FARTHER than the halo depth from their owners: fetched into a
+    # temporary block by one grouped send/recv (PartitionedArray._fetch_rows)
+    h0 = rng.integers(-9, 10, size=(31, 5)).astype(np.int64)
+    H = cn.array(h0)
+    assert isinstance(H._thunk, PartitionedArray)
+    assert np.array_equal((H[2:] + H[:-2]).__array__(), h0[2:] + h0[:-2])          # two rows apart
+    assert np.array_equal((H[7:] * H[:-7]).__array__(), h0[7:] * h0[:-7])          # crosses whole blocks
+    assert np.array_equal((H[0:-2, 1:-1] - H[2:, 1:-1]).__array__(), h0[0:-2, 1:-1] - h0[2:, 1:-1])
+    assert np.array_equal(cn.maximum(H[:5], H[-5:]).__array__(), np.maximum(h0[:5], h0[-5:]))
+    assert bool(cn.array_equal(H[3:], H[3:])) and not bool(cn.array_equal(H[3:], H[:-3]))
+    T = H[5:] + 1                       # a temporary tiled like rows 5.. of H
+    assert np.array_equal((T + H[:-5]).__array__(), h0[5:] + 1 + h0[:-5])
+    H[:-4] = H[4:] + 0
+    h0[:-4] = h0[4:] + 0
+    assert np.array_equal(H.__array__(), h0)
     # ---- random programs on partitioned arrays (the same text on every rank and for NumPy): shifted
     # views, temporaries, assignments into views, in-place updates, reductions fed back as operands.
     # int64 wrap-around arithmetic is exact, so every association order gives the same bits.
     for seed in range(int(os.environ.get("SIM_PROGRAMS", "6"))):
-        with np.errstate(over="ignore"):
-            got = partitioned_program(seed, cn)
-            exp = partitioned_program(seed, np)
-        assert len(got) == len(exp)
-        for i, (g, e) in enumerate(zip(got, exp)):
-            assert g.shape == e.shape and np.array_equal(g, e), \
-                f"rank {rank}: program {seed} value {i} differs (mode {mode}): {np.argwhere(g != e)[:3].tolist()}"
+        for free in (False, True):
+            with np.errstate(over="ignore"):
+                got = partitioned_program(seed, cn, free=free)
+                exp = partitioned_program(seed, np, free=free)
+            assert len(got) == len(exp)
+            for i, (g, e) in enumerate(zip(got, exp)):
+                assert g.shape == e.shape and np.array_equal(g, e), \
+                    f"rank {rank}: program {seed} (free={free}) value {i} differs (mode {mode}): " \
+                    f"{np.argwhere(g != e)[:3].tolist()}"
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")

@@ -7,11 +7,11 @@ CONVERT / UNARY_RED / SCALAR_UNARY_RED: operator dunders -> ufuncs (array.py:801
 (:1031-1037, :1668-1680).  Everything else of the 4.5 kLoC class is out of scope."""
 from __future__ import annotations
 
-from typing import Any, Optional, Sequence, Union
+from typing import Any, Optional
 
 import numpy as np
 
-from .config import ConvertCode, UnaryOpCode, UnaryRedCode, is_supported_dtype
+from .config import UnaryOpCode, UnaryRedCode, is_supported_dtype
 from .deferred import DeferredArray
 from .distributed import create_empty_thunk, thunk_from_numpy
 from .runtime import runtime

@@ -18,12 +18,12 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Any, List, Optional, Sequence, Tuple
+from typing import Any, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib, fusion
-from .config import BinaryOpCode, ConvertCode, UnaryOpCode, UnaryRedCode, dtype_code
+from .config import BinaryOpCode, ConvertCode, UnaryRedCode, dtype_code
 from .deferred import (_ARG_REDS, _UNARY_RED_IDENTITIES, DeferredArray, _basic_index,
                        launch_scalar_red)
 from .partition import RowPartition, plan_fetch, plan_halo

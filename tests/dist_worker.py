@@ -149,6 +149,19 @@ def main() -> None:
     assert not bool(cn.array_equal(X, Y))
     assert bool(cn.array_equal(X[1:-1], Y[1:-1]))  # shifted views: row fetch then local fold
 
+    # ---- operands farther than the halo depth from their owners (PartitionedArray._fetch_rows).  Added
+    # at the very end of round 2 with no GPU time left to run it: verified over gloo on the CPU
+    # stand-in (tests/sim_dist_worker.py); opt-in here until it has seen real NCCL once.
+    if os.environ.get("CNB_TEST_FAR_ROWS"):
+        h0 = rng.integers(-9, 10, size=(311, 17)).astype(np.int64)
+        H = cn.array(h0)
+        assert np.array_equal((H[2:] + H[:-2]).__array__(), h0[2:] + h0[:-2])
+        assert np.array_equal((H[97:] * H[:-97]).__array__(), h0[97:] * h0[:-97])
+        assert np.array_equal(cn.maximum(H[:5], H[-5:]).__array__(), np.maximum(h0[:5], h0[-5:]))
+        H[:-4] = H[4:] + 0
+        h0[:-4] = h0[4:] + 0
+        assert np.array_equal(H.__array__(), h0)
+
     cn.synchronize()
     dist.barrier()
     dist.destroy_process_group()
